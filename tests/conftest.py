@@ -1,0 +1,58 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _dec(v, dtype):
+    if isinstance(v, dict):
+        return np.array(v["re"], dtype=np.float64) + 1j * np.array(v["im"], dtype=np.float64)
+    return np.array(v, dtype=dtype)
+
+
+def load_fixtures():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")) as f:
+        raw = json.load(f)
+    out = []
+    for fx in raw["fixtures"]:
+        dt = np.complex128 if fx["dtype"] == "c128" else np.float64
+        c = dict(fx)
+        for k in ("V", "x", "y", "yT", "y_adj", "xT", "AT_dense", "dot_with", "dot_xy", "dot_xx"):
+            if k in c:
+                c[k] = _dec(c[k], dt).astype(dt)
+        out.append(c)
+    return out, raw["plans"]
+
+
+FIXTURES, PLAN_TABLES = load_fixtures()
+
+
+def fixture_matrix(fx):
+    """scipy CSR of a reference fixture, canonicalised like Julia's sparse(I,J,V,m,n)."""
+    import scipy.sparse as sp
+
+    A = sp.coo_matrix((fx["V"], (np.array(fx["I"]) - 1, np.array(fx["J"]) - 1)), shape=(fx["m"], fx["n"]))
+    A = sp.csr_matrix(A)
+    A.sum_duplicates()
+    A.sort_indices()
+    return A
+
+
+@pytest.fixture(scope="session")
+def fixtures():
+    return FIXTURES
+
+
+@pytest.fixture(scope="session")
+def plan_tables():
+    return PLAN_TABLES
