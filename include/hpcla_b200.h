@@ -1,0 +1,176 @@
+/* hpcla_b200.h — C ABI of libhpcla_b200.so: the B200 (sm_100a) device backend for the distributed sparse
+ * mat-vec hot path of HPCLinearAlgebra.jl (sloisel/LinearAlgebraMPI.jl).
+ *
+ * Every entry point names the reference interface it replaces (file:line under the reference tree).
+ * Conventions:
+ *   - plain pointers and sizes only; no C++/torch/Julia types cross this boundary;
+ *   - every function returns int, 0 = HPCLA_OK; the message of the last failure on the calling thread is
+ *     hpcla_last_error(); nothing here aborts or throws across the ABI (cf. the status checks of
+ *     ext/HPCLinearAlgebraCUDAExt.jl:247-251, 388-402);
+ *   - index arrays hold the reference's own 1-BASED values, in the reference's own width Ti (Int32 or Int64);
+ *     partitions and col_indices are Int64 as in the reference (Vector{Int});
+ *   - device arrays are BORROWED for the lifetime of the handle created from them (the caller keeps them rooted);
+ *     the library owns and frees only what it allocates itself;
+ *   - device work is enqueued on the caller's stream (cudaStream_t passed as void*) and the call returns after
+ *     enqueue, like the reference's _spmv! (src/sparse.jl:2081-2083); hpcla_ctx_sync() blocks;
+ *   - collective entry points must be called by all ranks in the same order (docs/src/api.md:5-6).
+ */
+#ifndef HPCLA_B200_H
+#define HPCLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPCLA_ABI_VERSION 1
+
+/* status codes */
+enum { HPCLA_OK = 0, HPCLA_ERR_ARG = 1, HPCLA_ERR_CUDA = 2, HPCLA_ERR_NCCL = 3, HPCLA_ERR_STATE = 4, HPCLA_ERR_NOMEM = 5 };
+/* element type T of HPCBackend{T,Ti,...} (src/backends.jl:137-141) */
+enum { HPCLA_F32 = 0, HPCLA_F64 = 1, HPCLA_C128 = 2 };
+/* index type Ti of HPCBackend{T,Ti,...} */
+enum { HPCLA_I32 = 0, HPCLA_I64 = 1 };
+
+typedef struct hpcla_ctx hpcla_ctx;     /* one rank <-> one GPU (ext/HPCLinearAlgebraCUDAExt.jl:611-613)          */
+typedef struct hpcla_csr hpcla_csr;     /* device view of one rank's HPCSparseMatrix (src/sparse.jl:319-337)       */
+typedef struct hpcla_planb hpcla_planb; /* VectorPlan under construction (between the two message rounds)          */
+typedef struct hpcla_plan hpcla_plan;   /* index fields of a VectorPlan (src/vectors.jl:229-251)                   */
+typedef struct hpcla_spmv hpcla_spmv;   /* (csr, plan) bound to device buffers: what `A*x` / `mul!` execute         */
+typedef struct hpcla_tb hpcla_tb;       /* TransposePlan under construction / its result (src/sparse.jl:1519-1538) */
+
+int hpcla_abi_version(void);
+const char* hpcla_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Context.  Replaces the device selection + NCCL bootstrap of ext/HPCLinearAlgebraCUDAExt.jl:370-443, 611-613.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Binds `device` (cudaSetDevice) to rank `rank` of `nranks`; creates the halo stream and events. */
+int hpcla_ctx_create(int device, int rank, int nranks, hpcla_ctx** out);
+/* ncclGetUniqueId (ext:388-393): 128 bytes, produced on rank 0 and broadcast by the host (MPI.Bcast! / torch). */
+int hpcla_nccl_unique_id(void* id128);
+/* ncclCommInitRank (ext:395-402).  Collective. */
+int hpcla_ctx_init_nccl(hpcla_ctx* ctx, const void* id128);
+/* Reuse the ncclComm_t the reference already caches per MPI communicator (ext:411-443). Not owned. */
+int hpcla_ctx_adopt_nccl(hpcla_ctx* ctx, void* nccl_comm);
+/* Single-process world: `n` contexts (ranks 0..n-1, any device assignment) exchange halos with device-to-device
+ * copies instead of NCCL.  This is the CommSerial-like harness mode (src/backends.jl:63) generalised to P ranks. */
+int hpcla_ctx_form_group(hpcla_ctx* const* ctxs, int n);
+int hpcla_ctx_sync(hpcla_ctx* ctx);
+void hpcla_ctx_destroy(hpcla_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Host-side structure (pure functions, no device).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* uniform_partition(n, nranks) — src/HPCLinearAlgebra.jl:279-289. partition_out[nranks+1], 1-based starts. */
+int hpcla_uniform_partition(int64_t n, int nranks, int64_t* partition_out);
+/* col_indices = unique!(sort(global cols)) and colval = searchsortedfirst(col_indices, g)
+ * — src/sparse.jl:501, 504 and compress_AT :137-144.
+ * global_cols: Ti[nnz] 1-based global columns; colval_out: Ti[nnz]; col_indices_out: capacity min(nnz, ncols_global). */
+int hpcla_compress_columns(int itype, int64_t nnz, const void* global_cols, int64_t ncols_global, void* colval_out,
+                           int64_t* col_indices_out, int64_t* ncols_compressed_out);
+
+/* VectorPlan(A, x) — src/sparse.jl:1875-1984 — split at its two message rounds so that the HOST does the
+ * communication (MPI in Julia, torch.distributed in the Python harness, plain moves in a single-process world):
+ *   begin    = Step 1 (:1886-1895) grouping of col_indices by owner in x.partition
+ *   counts   = the send_counts vector handed to the Alltoall (:1899-1900)
+ *   requests = the tag-20 message for `owner` (:1908-1918): ascending global indices wanted from it
+ *   finish   = Steps 4-7 (:1925-1957) given what the Alltoall and the tag-20 receives delivered. Consumes `pb`. */
+int hpcla_plan_begin(int rank, int nranks, const int64_t* col_indices, int64_t ncols_compressed,
+                     const int64_t* x_partition, hpcla_planb** out);
+int hpcla_planb_counts(const hpcla_planb* pb, int64_t* counts_out /* [nranks] */);
+int hpcla_planb_requests(const hpcla_planb* pb, int owner, int64_t* globals_out);
+int hpcla_plan_finish(hpcla_planb* pb, const int64_t* recv_counts /* [nranks] */,
+                      const int64_t* const* recv_lists /* [nranks], entry r = globals rank r wants from me */,
+                      hpcla_plan** out);
+/* Import a VectorPlan the reference already built (all fields of src/vectors.jl:229-251 that are indices).
+ * Index arrays are Ti (itype), rank ids Int64. n_x_local = length(x.v). */
+int hpcla_plan_import(int rank, int nranks, int itype, int64_t n_gathered, int64_t n_x_local, int64_t n_send,
+                      const int64_t* send_rank_ids, const int64_t* send_lens, const void* const* send_indices,
+                      int64_t n_recv, const int64_t* recv_rank_ids, const int64_t* recv_lens,
+                      const void* const* recv_perm, int64_t n_local, const void* local_src_indices,
+                      const void* local_dst_indices, hpcla_plan** out);
+/* Export, for bit-exact comparison.  field: 0 send_rank_ids, 1 recv_rank_ids, 2 local_src_indices,
+ * 3 local_dst_indices, 4 send_indices[slot], 5 recv_perm[slot]; values as Int64. */
+int hpcla_plan_len(const hpcla_plan* plan, int field, int64_t slot, int64_t* len_out);
+int hpcla_plan_get(const hpcla_plan* plan, int field, int64_t slot, int64_t* out);
+int hpcla_plan_n_gathered(const hpcla_plan* plan, int64_t* n_out);
+void hpcla_plan_destroy(hpcla_plan* plan);
+
+/* TransposePlan(A) + execute_plan!(plan, A) — src/sparse.jl:1551-1744, 1756-1829 — split at its message round
+ * (Alltoall of counts :1581-1583, tag-10 (row,col) pairs :1589-1624, tag-11 values :1770-1796):
+ *   begin   = Step 1: bucket every local nonzero by the owner of its column in col_partition
+ *   counts  = nonzeros destined to each rank (own rank included)
+ *   message = for `dest`: pairs (j = row of A^T, i = col of A^T) in the reference's send order, and the values
+ *   finish  = Steps 5-6 + compression: CSR of the owned rows of A^T, ascending columns, compressed, Ti indices
+ *   result  = copy out rowptr[nrows+1] (Ti), colval[nnz] (Ti), col_indices[ncc] (Int64), nzval[nnz] (T)        */
+int hpcla_transpose_begin(int rank, int nranks, int dtype, int itype, const int64_t* row_partition,
+                          const int64_t* col_partition, const void* h_rowptr, const void* h_colval,
+                          const int64_t* h_col_indices, const void* h_nzval, hpcla_tb** out);
+int hpcla_tb_counts(const hpcla_tb* tb, int64_t* counts_out /* [nranks] */);
+int hpcla_tb_message(const hpcla_tb* tb, int dest, int64_t* pairs_out /* [2*count] */, void* vals_out /* T[count] */);
+int hpcla_transpose_finish(hpcla_tb* tb, const int64_t* recv_counts, const int64_t* const* recv_pairs,
+                           const void* const* recv_vals, int64_t* nrows_out, int64_t* nnz_out, int64_t* ncc_out);
+int hpcla_tb_result(const hpcla_tb* tb, void* rowptr_out, void* colval_out, int64_t* col_indices_out, void* nzval_out);
+void hpcla_tb_destroy(hpcla_tb* tb);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Device objects.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Device view of A: borrows A.rowptr_target / A.colval_target / A.nzval (src/sparse.jl:334-335, 519-520), 1-based
+ * contents, unchanged.  Builds the row-tile table used by the kernels (no copy of the matrix is made; in-place value
+ * writes to A.nzval — src/indexing.jl:932-982 — are seen by the next multiply). */
+int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nrows_local, int64_t ncols_compressed, int64_t nnz,
+                     const void* d_rowptr, const void* d_colval, const void* d_nzval, hpcla_csr** out);
+/* query: number of row tiles, rows longer than the split threshold */
+int hpcla_csr_info(const hpcla_csr* csr, int64_t* ntiles_out, int64_t* nlong_rows_out);
+void hpcla_csr_destroy(hpcla_csr* csr);
+
+/* Binds (A, VectorPlan) to device buffers: the device copy of send indices, the packed send buffer, `gathered`
+ * (src/sparse.jl:1972) and the interior/boundary tile lists.  n_x_local = length(x.v) on this rank.  In a
+ * single-process world all ranks must create their operators in the same order (they are paired by sequence). */
+int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* csr, const hpcla_plan* plan, int64_t n_x_local, hpcla_spmv** out);
+/* y.v = A * x — replaces execute_plan! (src/vectors.jl:394-463) + _spmv! (src/sparse.jl:2075-2084), i.e. the body
+ * of Base.:*(A, x) (src/sparse.jl:2096-2128) and of mul!(y, A, x) (:2019-2037).  d_x = x.v, d_y = y.v (device).
+ * NCCL world or nranks == 1: one call does everything (collective).  Enqueue only. */
+int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
+/* Single-process world: call begin on every rank, then finish on every rank. */
+int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
+int hpcla_spmv_finish(hpcla_spmv* op);
+/* Parity hook: fills plan.gathered exactly as execute_plan! would and returns its device address
+ * (gathered[d] == x_global[col_indices[d]]).  Same calling discipline as run (NCCL) / begin+finish (group: this is
+ * the begin half; hpcla_spmv_gather_finish the other). */
+int hpcla_spmv_gather(hpcla_spmv* op, const void* d_x, void* stream, void** d_gathered_out);
+int hpcla_spmv_gather_finish(hpcla_spmv* op);
+/* introspection for tests/benchmarks: counts of interior and boundary tiles, whether x.v is read in place */
+int hpcla_spmv_info(const hpcla_spmv* op, int64_t* n_interior_tiles, int64_t* n_boundary_tiles, int* x_in_place,
+                    int* sends_contiguous);
+/* kernel launches enqueued by this operator so far (bench.py's gpu_launches) */
+int64_t hpcla_spmv_launch_count(const hpcla_spmv* op);
+void hpcla_spmv_destroy(hpcla_spmv* op);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * HPCVector reductions and updates used by iterative solvers.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* dot(x, y) — src/vectors.jl:798-812: local dot (conjugating x for complex) + Allreduce(+).  result_out: T on the
+ * host (2 doubles for C128).  Blocking (the reference returns a host scalar too).  Collective in an NCCL world;
+ * in a single-process world it returns the LOCAL dot and the host adds the ranks. */
+int hpcla_dot(hpcla_ctx* ctx, int dtype, int64_t n, const void* d_x, const void* d_y, void* result_out, void* stream);
+/* norm(v) — src/vectors.jl:758-766: sqrt(Allreduce(+)(local_norm^2)); result_out: double (float for F32).
+ * Single-process world: returns the local SUM OF SQUARES instead (host adds and takes the root). */
+int hpcla_nrm2(hpcla_ctx* ctx, int dtype, int64_t n, const void* d_x, void* result_out, void* stream);
+/* y .= alpha .* x .+ beta .* y — the fused broadcast of src/vectors.jl:1203-1221; alpha, beta: T on the host. */
+int hpcla_axpby(hpcla_ctx* ctx, int dtype, int64_t n, const void* alpha, const void* d_x, const void* beta, void* d_y,
+                void* stream);
+/* Fixed-iteration conjugate gradients composed from the operations above (the reference ships no CG):
+ * x0 = 0, r = b, p = r; iters times { q = A p; alpha = rr/dot(p,q); x += alpha p; r -= alpha q; rr' = dot(r,r);
+ * p = r + (rr'/rr) p }.  All scalars stay on the device; no host synchronisation inside the loop.  F32/F64 only.
+ * work: device scratch of 3*n elements (r, p, q).  rr_history_out: host double[iters] (may be NULL), filled after a
+ * final synchronisation.  NCCL world or nranks == 1. */
+int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work, int iters, double* rr_history_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPCLA_B200_H */

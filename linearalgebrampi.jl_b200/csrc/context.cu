@@ -1,0 +1,841 @@
+// context.cu — contexts, the NCCL / single-process halo exchange, and the orchestration of one multiply:
+//   pack (halo stream) -> grouped ncclSend/ncclRecv straight into the ghost segments of `gathered` (halo stream)
+//   || interior row tiles (caller's stream)  ->  wait  ->  boundary row tiles + split long rows.
+// Replaces execute_plan! (src/vectors.jl:394-463: host-staged Isend/Irecv with a D2H copy of x and an H2D copy of
+// `gathered` per call) and the launch in Base.:*(A, x) / mul! (src/sparse.jl:2096-2128, 2019-2037).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "device.h"
+
+using namespace hpcla;
+
+#define CU_TRY(expr)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) return fail(HPCLA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL, resolved at run time: the process that loaded torch already has libnccl.so.2 mapped and dlopen returns that
+// copy; a Julia process gets NCCL_jll's.  Nothing here needs NCCL until a multi-rank context asks for it.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) {
+            api.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+            return;
+        }
+#define LOAD(field, sym)                                          \
+    api.field = (decltype(api.field))dlsym(api.handle, sym);      \
+    if (!api.field) api.error = std::string("libnccl lacks ") + sym;
+        LOAD(GetUniqueId, "ncclGetUniqueId")
+        LOAD(CommInitRank, "ncclCommInitRank")
+        LOAD(CommDestroy, "ncclCommDestroy")
+        LOAD(Send, "ncclSend")
+        LOAD(Recv, "ncclRecv")
+        LOAD(GroupStart, "ncclGroupStart")
+        LOAD(GroupEnd, "ncclGroupEnd")
+        LOAD(AllReduce, "ncclAllReduce")
+        LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    });
+    return &api;
+}
+}  // namespace
+
+#define NCCL_TRY(expr)                                                                                             \
+    do {                                                                                                           \
+        ncclResult_t _r = (expr);                                                                                  \
+        if (_r != ncclSuccess) return fail(HPCLA_ERR_NCCL, "%s failed: %s", #expr, nccl_api()->GetErrorString(_r)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+struct hpcla_group {
+    std::mutex mu;  // rank-threads register and look up operators concurrently
+    std::vector<hpcla_ctx*> ctxs;
+    std::vector<std::vector<hpcla_spmv*>> ops;  // [sequence][rank]
+    int refs = 0;
+};
+
+struct hpcla_ctx {
+    int device = 0, rank = 0, nranks = 1;
+    cudaStream_t halo_stream = nullptr;
+    ncclComm_t comm = nullptr;
+    bool comm_owned = false;
+    hpcla_group* group = nullptr;
+    i64 op_seq = 0;
+    double* d_red_scratch = nullptr;  // reduce_scratch_doubles()
+    double* d_red_out = nullptr;      // 8 doubles
+    double* h_red_out = nullptr;      // pinned, 8 doubles
+};
+
+struct hpcla_csr {
+    hpcla_ctx* ctx = nullptr;
+    int dtype = 0, itype = 0;
+    i64 nrows = 0, ncc = 0, nnz = 0;
+    const void *d_rowptr = nullptr, *d_colval = nullptr, *d_nzval = nullptr;  // borrowed
+    TileShape shape{};
+    TileDesc* d_tiles = nullptr;
+    i64 ntiles = 0;
+    i64 long_threshold = 0, chunk_nnz = 0;
+    i64 nlong = 0, nchunks = 0;
+    i64 *d_long_rows = nullptr, *d_chunk_ptr = nullptr;
+    void* d_partials = nullptr;
+};
+
+struct Seg {
+    int peer;
+    i64 start;   // recv: 1-based first position in gathered; send: offset (elements) into the packed send buffer
+    i64 count;
+    bool contiguous;  // send only: the requested local indices are src0, src0+1, ...
+    i64 src0;         // send only: first 1-based local index
+};
+
+struct hpcla_spmv {
+    hpcla_ctx* ctx = nullptr;
+    hpcla_csr* csr = nullptr;
+    hpcla_plan plan;  // private copy of the index fields
+    i64 n_x_local = 0;
+    i64 seq = 0;
+    // own segment of gathered
+    i64 own_lo = 1, own_n = 0, own_src0 = 1;
+    bool x_in_place = true;  // own columns read straight from x.v
+    bool has_ghost = false;
+    bool has_peers = false;
+    std::vector<Seg> sends, recvs;
+    bool sends_contiguous = true;
+    i64 total_send = 0;
+    void* d_gathered = nullptr;
+    void* d_sendbuf = nullptr;
+    i64* d_send_idx = nullptr;                              // concatenated send_indices (all peers)
+    i64 *d_local_src = nullptr, *d_local_dst = nullptr;     // only when needed (fallback / gather hook)
+    int *d_list_int = nullptr, *d_list_bnd = nullptr;
+    int n_int = 0, n_bnd = 0;
+    cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
+    bool halo_recorded = false;
+    // in-flight call
+    const void* cur_x = nullptr;
+    void* cur_y = nullptr;
+    cudaStream_t cur_stream = nullptr;
+    int phase = 0;  // 0 idle, 1 multiply begun, 2 gather begun
+    i64 launches = 0;
+};
+
+static int set_device(const hpcla_ctx* ctx) {
+    CU_TRY(cudaSetDevice(ctx->device));
+    return HPCLA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int hpcla_ctx_create(int device, int rank, int nranks, hpcla_ctx** out) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(HPCLA_ERR_ARG, "hpcla_ctx_create: bad arguments");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(HPCLA_ERR_CUDA, "hpcla_ctx_create: no CUDA device is visible (%s); this backend has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(HPCLA_ERR_ARG, "hpcla_ctx_create: device %d out of range (%d visible)", device, ndev);
+    CU_TRY(cudaSetDevice(device));
+    hpcla_ctx* c = new hpcla_ctx();
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    CU_TRY(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaMalloc(&c->d_red_scratch, sizeof(double) * reduce_scratch_doubles()));
+    CU_TRY(cudaMemset(c->d_red_scratch, 0, sizeof(double) * reduce_scratch_doubles()));
+    CU_TRY(cudaMalloc(&c->d_red_out, sizeof(double) * 8));
+    CU_TRY(cudaMallocHost(&c->h_red_out, sizeof(double) * 8));
+    *out = c;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_nccl_unique_id(void* id128) {
+    NcclApi* api = nccl_api();
+    if (!api->error.empty()) return fail(HPCLA_ERR_NCCL, "%s", api->error.c_str());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(api->GetUniqueId(&id));
+    std::memcpy(id128, &id, 128);
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_ctx_init_nccl(hpcla_ctx* ctx, const void* id128) {
+    if (!ctx || !id128) return fail(HPCLA_ERR_ARG, "hpcla_ctx_init_nccl: null");
+    if (ctx->comm || ctx->group) return fail(HPCLA_ERR_STATE, "hpcla_ctx_init_nccl: the context already has a world");
+    NcclApi* api = nccl_api();
+    if (!api->error.empty()) return fail(HPCLA_ERR_NCCL, "%s", api->error.c_str());
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    NCCL_TRY(api->CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank));
+    ctx->comm_owned = true;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_ctx_adopt_nccl(hpcla_ctx* ctx, void* nccl_comm) {
+    if (!ctx || !nccl_comm) return fail(HPCLA_ERR_ARG, "hpcla_ctx_adopt_nccl: null");
+    if (ctx->comm || ctx->group) return fail(HPCLA_ERR_STATE, "hpcla_ctx_adopt_nccl: the context already has a world");
+    NcclApi* api = nccl_api();
+    if (!api->error.empty()) return fail(HPCLA_ERR_NCCL, "%s", api->error.c_str());
+    ctx->comm = (ncclComm_t)nccl_comm;
+    ctx->comm_owned = false;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_ctx_form_group(hpcla_ctx* const* ctxs, int n) {
+    if (!ctxs || n < 1) return fail(HPCLA_ERR_ARG, "hpcla_ctx_form_group: bad arguments");
+    for (int r = 0; r < n; ++r) {
+        if (!ctxs[r] || ctxs[r]->rank != r || ctxs[r]->nranks != n) return fail(HPCLA_ERR_ARG, "hpcla_ctx_form_group: contexts must be ranks 0..n-1 of an n-rank world, in order");
+        if (ctxs[r]->comm || ctxs[r]->group) return fail(HPCLA_ERR_STATE, "hpcla_ctx_form_group: context %d already has a world", r);
+    }
+    for (int a = 0; a < n; ++a)  // peer access for cross-device copies (same device: nothing to do)
+        for (int b = 0; b < n; ++b)
+            if (ctxs[a]->device != ctxs[b]->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ctxs[a]->device, ctxs[b]->device);
+                if (can) {
+                    cudaSetDevice(ctxs[a]->device);
+                    cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[b]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(HPCLA_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+                    cudaGetLastError();
+                }
+            }
+    hpcla_group* g = new hpcla_group();
+    g->ctxs.assign(ctxs, ctxs + n);
+    g->refs = n;
+    for (int r = 0; r < n; ++r) ctxs[r]->group = g;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_ctx_sync(hpcla_ctx* ctx) {
+    if (!ctx) return fail(HPCLA_ERR_ARG, "hpcla_ctx_sync: null");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CU_TRY(cudaDeviceSynchronize());
+    return HPCLA_OK;
+}
+
+extern "C" void hpcla_ctx_destroy(hpcla_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->comm && ctx->comm_owned) nccl_api()->CommDestroy(ctx->comm);
+    if (ctx->group && --ctx->group->refs == 0) delete ctx->group;
+    if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);
+    cudaFree(ctx->d_red_scratch);
+    cudaFree(ctx->d_red_out);
+    cudaFreeHost(ctx->h_red_out);
+    delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CSR view
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nrows, int64_t ncc, int64_t nnz, const void* d_rowptr,
+                                const void* d_colval, const void* d_nzval, hpcla_csr** out) {
+    if (!ctx || !out || nrows < 0 || ncc < 0 || nnz < 0 || !d_rowptr) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: bad arguments");
+    if (!dtype_size(dtype) || !itype_size(itype)) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: unknown dtype/itype");
+    if (nnz > 0 && (!d_colval || !d_nzval)) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: null colval/nzval");
+    if (((uintptr_t)d_colval & 15) || ((uintptr_t)d_nzval & 15))
+        return fail(HPCLA_ERR_ARG, "hpcla_csr_create: colval and nzval must be 16-byte aligned (128-bit loads)");
+    if (itype == HPCLA_I32 && nnz >= (i64)INT32_MAX) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: nnz does not fit Int32 row pointers");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    hpcla_csr* A = new hpcla_csr();
+    A->ctx = ctx;
+    A->dtype = dtype;
+    A->itype = itype;
+    A->nrows = nrows;
+    A->ncc = ncc;
+    A->nnz = nnz;
+    A->d_rowptr = d_rowptr;
+    A->d_colval = d_colval;
+    A->d_nzval = d_nzval;
+    A->shape = tile_shape(dtype);
+    A->ntiles = nnz / A->shape.window + 1;
+    if (A->ntiles >= (i64)INT32_MAX) {
+        delete A;
+        return fail(HPCLA_ERR_ARG, "hpcla_csr_create: too many tiles");
+    }
+    A->long_threshold = 16384;
+    A->chunk_nnz = 16384;
+    cudaStream_t st = ctx->halo_stream;
+    CU_TRY(cudaMalloc(&A->d_tiles, sizeof(TileDesc) * (size_t)(A->ntiles + 1)));
+    CU_TRY(launch_build_tiles(itype, d_rowptr, nrows, nnz, A->shape.window, A->d_tiles, A->ntiles, st));
+    // rows longer than the split threshold (rare: power-law tails)
+    const i64 cap = nnz / A->long_threshold + 1;
+    unsigned long long* d_count = nullptr;
+    i64* d_rows = nullptr;
+    CU_TRY(cudaMalloc(&d_count, sizeof(unsigned long long)));
+    CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    CU_TRY(cudaMalloc(&d_rows, sizeof(i64) * (size_t)cap));
+    CU_TRY(launch_find_long_rows(itype, d_rowptr, nrows, A->long_threshold, d_rows, cap, d_count, st));
+    unsigned long long count = 0;
+    CU_TRY(cudaMemcpyAsync(&count, d_count, sizeof count, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaFree(d_count);
+    A->nlong = (i64)count;
+    if (A->nlong > 0) {
+        std::vector<i64> rows((size_t)A->nlong);
+        CU_TRY(cudaMemcpy(rows.data(), d_rows, sizeof(i64) * rows.size(), cudaMemcpyDeviceToHost));
+        std::sort(rows.begin(), rows.end());
+        // row lengths: two row-pointer reads per long row
+        std::vector<i64> chunk_ptr((size_t)A->nlong + 1, 0);
+        const size_t is = itype_size(itype);
+        for (i64 i = 0; i < A->nlong; ++i) {
+            char two[16];
+            CU_TRY(cudaMemcpy(two, (const char*)d_rowptr + (size_t)rows[(size_t)i] * is, 2 * is, cudaMemcpyDeviceToHost));
+            i64 b = is == 4 ? (i64)((int32_t*)two)[0] : ((i64*)two)[0];
+            i64 e = is == 4 ? (i64)((int32_t*)two)[1] : ((i64*)two)[1];
+            chunk_ptr[(size_t)i + 1] = chunk_ptr[(size_t)i] + (e - b + A->chunk_nnz - 1) / A->chunk_nnz;
+        }
+        A->nchunks = chunk_ptr.back();
+        CU_TRY(cudaMalloc(&A->d_long_rows, sizeof(i64) * rows.size()));
+        CU_TRY(cudaMalloc(&A->d_chunk_ptr, sizeof(i64) * chunk_ptr.size()));
+        CU_TRY(cudaMalloc(&A->d_partials, dtype_size(dtype) * (size_t)A->nchunks));
+        CU_TRY(cudaMemcpy(A->d_long_rows, rows.data(), sizeof(i64) * rows.size(), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(A->d_chunk_ptr, chunk_ptr.data(), sizeof(i64) * chunk_ptr.size(), cudaMemcpyHostToDevice));
+    }
+    cudaFree(d_rows);
+    *out = A;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_csr_info(const hpcla_csr* A, int64_t* ntiles_out, int64_t* nlong_out) {
+    if (!A) return fail(HPCLA_ERR_ARG, "hpcla_csr_info: null");
+    if (ntiles_out) *ntiles_out = A->ntiles;
+    if (nlong_out) *nlong_out = A->nlong;
+    return HPCLA_OK;
+}
+
+extern "C" void hpcla_csr_destroy(hpcla_csr* A) {
+    if (!A) return;
+    cudaSetDevice(A->ctx->device);
+    cudaFree(A->d_tiles);
+    cudaFree(A->d_long_rows);
+    cudaFree(A->d_chunk_ptr);
+    cudaFree(A->d_partials);
+    delete A;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bound operator
+// ---------------------------------------------------------------------------------------------------------------
+static bool is_consecutive(const std::vector<i64>& v) {
+    for (size_t k = 1; k < v.size(); ++k)
+        if (v[k] != v[k - 1] + 1) return false;
+    return true;
+}
+
+extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan* plan, int64_t n_x_local, hpcla_spmv** out) {
+    if (!ctx || !A || !plan || !out || n_x_local < 0) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: bad arguments");
+    if (A->ctx != ctx) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: the matrix belongs to another context");
+    if (plan->n_gathered != A->ncc) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: plan gathers %lld elements but A has %lld compressed columns", (long long)plan->n_gathered, (long long)A->ncc);
+    if (plan->rank != ctx->rank || plan->nranks != ctx->nranks) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: plan was built for rank %d of %d", plan->rank, plan->nranks);
+    if (plan->n_x_local >= 0 && plan->n_x_local != n_x_local) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: x.v has %lld elements, the plan expects %lld", (long long)n_x_local, (long long)plan->n_x_local);
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    const size_t es = dtype_size(A->dtype);
+    hpcla_spmv* op = new hpcla_spmv();
+    op->ctx = ctx;
+    op->csr = A;
+    op->plan = *plan;
+    op->n_x_local = n_x_local;
+    const hpcla_plan& P = op->plan;
+    // validate what the kernels rely on
+    for (i64 v : P.local_src)
+        if (v < 1 || v > n_x_local) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: local_src index out of range"); }
+    for (auto& s : P.send_indices)
+        for (i64 v : s)
+            if (v < 1 || v > n_x_local) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: send index out of range"); }
+    if (!is_consecutive(P.local_dst)) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: local_dst_indices must be a consecutive range (col_indices sorted, contiguous partition)"); }
+    for (auto& s : P.recv_perm)
+        if (s.empty() || !is_consecutive(s)) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: every recv_perm must be a non-empty consecutive range"); }
+    // every position of gathered must be produced exactly once
+    {
+        i64 covered = (i64)P.local_dst.size();
+        for (auto& s : P.recv_perm) covered += (i64)s.size();
+        if (covered != P.n_gathered) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: plan covers %lld of %lld gathered positions", (long long)covered, (long long)P.n_gathered); }
+    }
+    op->own_n = (i64)P.local_dst.size();
+    op->own_lo = op->own_n ? P.local_dst[0] : 1;
+    op->own_src0 = op->own_n ? P.local_src[0] : 1;
+    op->x_in_place = is_consecutive(P.local_src);
+    op->has_ghost = !P.recv_perm.empty();
+    op->has_peers = !P.recv_rank_ids.empty() || !P.send_rank_ids.empty();
+    if (op->has_peers && !ctx->comm && !ctx->group && ctx->nranks > 1) { delete op; return fail(HPCLA_ERR_STATE, "hpcla_spmv_create: the plan exchanges data but the context has neither an NCCL communicator nor a single-process group"); }
+    for (size_t i = 0; i < P.recv_rank_ids.size(); ++i) op->recvs.push_back(Seg{(int)P.recv_rank_ids[i], P.recv_perm[i][0], (i64)P.recv_perm[i].size(), true, 0});
+    i64 off = 0;
+    for (size_t i = 0; i < P.send_rank_ids.size(); ++i) {
+        const bool contig = is_consecutive(P.send_indices[i]);
+        op->sends.push_back(Seg{(int)P.send_rank_ids[i], off, (i64)P.send_indices[i].size(), contig, P.send_indices[i].empty() ? 1 : P.send_indices[i][0]});
+        op->sends_contiguous = op->sends_contiguous && contig;
+        off += (i64)P.send_indices[i].size();
+    }
+    op->total_send = off;
+    if (op->has_ghost || !op->x_in_place) {
+        CU_TRY(cudaMalloc(&op->d_gathered, es * (size_t)std::max<i64>(P.n_gathered, 1)));
+        CU_TRY(cudaMemset(op->d_gathered, 0, es * (size_t)std::max<i64>(P.n_gathered, 1)));
+    }
+    if (op->total_send > 0) {
+        CU_TRY(cudaMalloc(&op->d_sendbuf, es * (size_t)op->total_send));
+        std::vector<i64> idx;
+        idx.reserve((size_t)op->total_send);
+        for (auto& s : P.send_indices) idx.insert(idx.end(), s.begin(), s.end());
+        CU_TRY(cudaMalloc(&op->d_send_idx, sizeof(i64) * idx.size()));
+        CU_TRY(cudaMemcpy(op->d_send_idx, idx.data(), sizeof(i64) * idx.size(), cudaMemcpyHostToDevice));
+    }
+    if (!op->x_in_place && op->own_n > 0) {
+        CU_TRY(cudaMalloc(&op->d_local_src, sizeof(i64) * (size_t)op->own_n));
+        CU_TRY(cudaMalloc(&op->d_local_dst, sizeof(i64) * (size_t)op->own_n));
+        CU_TRY(cudaMemcpy(op->d_local_src, P.local_src.data(), sizeof(i64) * (size_t)op->own_n, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(op->d_local_dst, P.local_dst.data(), sizeof(i64) * (size_t)op->own_n, cudaMemcpyHostToDevice));
+    }
+    CU_TRY(cudaEventCreateWithFlags(&op->ev_x, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&op->ev_packed, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
+    // interior / boundary tile lists: a tile is boundary iff one of its stored columns is a ghost
+    if (op->has_ghost && A->ntiles > 0) {
+        unsigned char* d_flags = nullptr;
+        CU_TRY(cudaMalloc(&d_flags, (size_t)A->ntiles));
+        CU_TRY(launch_classify_tiles(A->itype, A->d_colval, A->d_tiles, A->ntiles, op->own_lo, op->own_n, d_flags, ctx->halo_stream));
+        std::vector<unsigned char> flags((size_t)A->ntiles);
+        CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, flags.size(), cudaMemcpyDeviceToHost, ctx->halo_stream));
+        CU_TRY(cudaStreamSynchronize(ctx->halo_stream));
+        cudaFree(d_flags);
+        std::vector<int> li, lb;
+        for (i64 t = 0; t < A->ntiles; ++t) (flags[(size_t)t] ? lb : li).push_back((int)t);
+        op->n_int = (int)li.size();
+        op->n_bnd = (int)lb.size();
+        if (op->n_int) {
+            CU_TRY(cudaMalloc(&op->d_list_int, sizeof(int) * li.size()));
+            CU_TRY(cudaMemcpy(op->d_list_int, li.data(), sizeof(int) * li.size(), cudaMemcpyHostToDevice));
+        }
+        if (op->n_bnd) {
+            CU_TRY(cudaMalloc(&op->d_list_bnd, sizeof(int) * lb.size()));
+            CU_TRY(cudaMemcpy(op->d_list_bnd, lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice));
+        }
+    } else {
+        op->n_int = (int)A->ntiles;
+        op->n_bnd = 0;
+    }
+    op->seq = ctx->op_seq++;
+    if (ctx->group) {
+        hpcla_group* g = ctx->group;
+        std::lock_guard<std::mutex> lk(g->mu);
+        if ((i64)g->ops.size() <= op->seq) g->ops.resize((size_t)op->seq + 1, std::vector<hpcla_spmv*>(g->ctxs.size(), nullptr));
+        g->ops[(size_t)op->seq][(size_t)ctx->rank] = op;
+    }
+    *out = op;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_info(const hpcla_spmv* op, int64_t* n_int, int64_t* n_bnd, int* x_in_place, int* sends_contiguous) {
+    if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_info: null");
+    if (n_int) *n_int = op->n_int;
+    if (n_bnd) *n_bnd = op->n_bnd;
+    if (x_in_place) *x_in_place = op->x_in_place ? 1 : 0;
+    if (sends_contiguous) *sends_contiguous = op->sends_contiguous ? 1 : 0;
+    return HPCLA_OK;
+}
+extern "C" int64_t hpcla_spmv_launch_count(const hpcla_spmv* op) { return op ? op->launches : -1; }
+
+extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
+    if (!op) return;
+    cudaSetDevice(op->ctx->device);
+    cudaDeviceSynchronize();
+    if (op->ctx->group) {
+        hpcla_group* g = op->ctx->group;
+        std::lock_guard<std::mutex> lk(g->mu);
+        if ((i64)g->ops.size() > op->seq) g->ops[(size_t)op->seq][(size_t)op->ctx->rank] = nullptr;
+    }
+    cudaFree(op->d_gathered);
+    cudaFree(op->d_sendbuf);
+    cudaFree(op->d_send_idx);
+    cudaFree(op->d_local_src);
+    cudaFree(op->d_local_dst);
+    cudaFree(op->d_list_int);
+    cudaFree(op->d_list_bnd);
+    if (op->ev_x) cudaEventDestroy(op->ev_x);
+    if (op->ev_packed) cudaEventDestroy(op->ev_packed);
+    if (op->ev_halo) cudaEventDestroy(op->ev_halo);
+    delete op;
+}
+
+static ncclDataType_t nccl_type(int dtype, size_t* per_elem) {
+    if (dtype == HPCLA_F32) { *per_elem = 1; return ncclFloat32; }
+    if (dtype == HPCLA_F64) { *per_elem = 1; return ncclFloat64; }
+    *per_elem = 2;
+    return ncclFloat64;  // ComplexF64 travels as interleaved (re, im) doubles
+}
+
+static hpcla_spmv* group_peer(const hpcla_spmv* op, int peer) {
+    hpcla_group* g = op->ctx->group;
+    if (!g) return nullptr;
+    std::lock_guard<std::mutex> lk(g->mu);
+    if ((i64)g->ops.size() <= op->seq) return nullptr;
+    return g->ops[(size_t)op->seq][(size_t)peer];
+}
+
+// Send half of the exchange, on the halo stream: wait for x, pack what is not contiguous, and (NCCL world) post the
+// grouped send/recv pairs so that ghosts land directly in their segments of `gathered` (no unpack: SURVEY §0.7).
+static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream) {
+    hpcla_ctx* ctx = op->ctx;
+    const int dtype = op->csr->dtype;
+    const size_t es = dtype_size(dtype);
+    cudaStream_t hs = ctx->halo_stream;
+    CU_TRY(cudaEventRecord(op->ev_x, stream));
+    CU_TRY(cudaStreamWaitEvent(hs, op->ev_x, 0));
+    const bool group = ctx->group != nullptr;
+    if (group) {
+        // my packed buffer may still be read by a peer's copy of the previous multiply
+        for (const Seg& s : op->sends) {
+            hpcla_spmv* peer = group_peer(op, s.peer);
+            if (peer && peer->halo_recorded) CU_TRY(cudaStreamWaitEvent(hs, peer->ev_halo, 0));
+        }
+    }
+    if (op->total_send > 0) {
+        if (group) {  // single-process world: peers copy out of my packed buffer, so everything is staged there
+            if (op->sends_contiguous) {
+                for (const Seg& s : op->sends)
+                    CU_TRY(cudaMemcpyAsync((char*)op->d_sendbuf + (size_t)s.start * es, (const char*)d_x + (size_t)(s.src0 - 1) * es, (size_t)s.count * es, cudaMemcpyDeviceToDevice, hs));
+            } else {
+                CU_TRY(launch_pack(dtype, d_x, op->d_send_idx, op->total_send, op->d_sendbuf, hs));
+                op->launches += 1;
+            }
+        } else if (!op->sends_contiguous) {
+            CU_TRY(launch_pack(dtype, d_x, op->d_send_idx, op->total_send, op->d_sendbuf, hs));
+            op->launches += 1;
+        }
+    }
+    CU_TRY(cudaEventRecord(op->ev_packed, hs));
+    if (!group && ctx->comm) {
+        NcclApi* api = nccl_api();
+        size_t per = 1;
+        const ncclDataType_t nt = nccl_type(dtype, &per);
+        NCCL_TRY(api->GroupStart());
+        for (const Seg& s : op->sends) {
+            // all runs contiguous in x.v (every stencil): send straight from x, no pack kernel, no copy
+            const char* src = op->sends_contiguous ? (const char*)d_x + (size_t)(s.src0 - 1) * es : (const char*)op->d_sendbuf + (size_t)s.start * es;
+            NCCL_TRY(api->Send(src, (size_t)s.count * per, nt, s.peer, ctx->comm, hs));
+        }
+        for (const Seg& r : op->recvs) NCCL_TRY(api->Recv((char*)op->d_gathered + (size_t)(r.start - 1) * es, (size_t)r.count * per, nt, r.peer, ctx->comm, hs));
+        NCCL_TRY(api->GroupEnd());
+        CU_TRY(cudaEventRecord(op->ev_halo, hs));
+        op->halo_recorded = true;
+    }
+    return HPCLA_OK;
+}
+
+// Receive half for a single-process world: copy each peer's packed run into my ghost segment.
+static int exchange_finish_group(hpcla_spmv* op) {
+    hpcla_ctx* ctx = op->ctx;
+    const size_t es = dtype_size(op->csr->dtype);
+    cudaStream_t hs = ctx->halo_stream;
+    for (const Seg& r : op->recvs) {
+        hpcla_spmv* peer = group_peer(op, r.peer);
+        if (!peer || peer->phase == 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_finish: rank %d has not begun the matching multiply", r.peer);
+        const Seg* ps = nullptr;
+        for (const Seg& s : peer->sends)
+            if (s.peer == ctx->rank) ps = &s;
+        if (!ps || ps->count != r.count) return fail(HPCLA_ERR_STATE, "hpcla_spmv_finish: rank %d sends %lld elements to rank %d, which expects %lld", r.peer, ps ? (long long)ps->count : 0LL, ctx->rank, (long long)r.count);
+        CU_TRY(cudaStreamWaitEvent(hs, peer->ev_packed, 0));
+        CU_TRY(cudaMemcpyAsync((char*)op->d_gathered + (size_t)(r.start - 1) * es, (const char*)peer->d_sendbuf + (size_t)ps->start * es, (size_t)r.count * es, cudaMemcpyDefault, hs));
+    }
+    CU_TRY(cudaEventRecord(op->ev_halo, hs));
+    op->halo_recorded = true;
+    return HPCLA_OK;
+}
+
+static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, void* d_y) {
+    const hpcla_csr* A = op->csr;
+    const size_t es = dtype_size(A->dtype);
+    L.dtype = A->dtype;
+    L.itype = A->itype;
+    L.rowptr = A->d_rowptr;
+    L.colval = A->d_colval;
+    L.nzval = A->d_nzval;
+    L.nrows = A->nrows;
+    L.nnz = A->nnz;
+    L.tiles = A->d_tiles;
+    L.x_own = op->x_in_place ? (const void*)((const char*)d_x + (size_t)(op->own_src0 - 1) * es)
+                             : (const void*)((const char*)op->d_gathered + (size_t)(op->own_lo - 1) * es);
+    L.gathered = op->d_gathered;
+    L.own_lo = op->own_lo;
+    L.own_n = op->own_n;
+    L.has_ghost = op->has_ghost;
+    L.y = d_y;
+    L.long_threshold = A->long_threshold;
+}
+
+static int launch_long(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stream) {
+    const hpcla_csr* A = op->csr;
+    if (A->nlong == 0) return HPCLA_OK;
+    LongRowsLaunch LL;
+    LL.dtype = A->dtype;
+    LL.itype = A->itype;
+    LL.rowptr = A->d_rowptr;
+    LL.colval = A->d_colval;
+    LL.nzval = A->d_nzval;
+    LL.long_rows = A->d_long_rows;
+    LL.chunk_ptr = A->d_chunk_ptr;
+    LL.nlong = A->nlong;
+    LL.nchunks = A->nchunks;
+    LL.chunk_nnz = A->chunk_nnz;
+    LL.x_own = base.x_own;
+    LL.gathered = base.gathered;
+    LL.own_lo = base.own_lo;
+    LL.own_n = base.own_n;
+    LL.has_ghost = base.has_ghost;
+    LL.partials = A->d_partials;
+    LL.y = base.y;
+    CU_TRY(launch_long_rows(LL, stream));
+    op->launches += 2;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream_) {
+    if (!op || (op->n_x_local > 0 && !d_x) || (op->csr->nrows > 0 && !d_y)) return fail(HPCLA_ERR_ARG, "hpcla_spmv_begin: null");
+    if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_begin: the previous call was not finished");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    op->cur_x = d_x;
+    op->cur_y = d_y;
+    op->cur_stream = stream;
+    if (op->has_peers) {
+        rc = exchange_begin(op, d_x, stream);
+        if (rc) return rc;
+    }
+    if (!op->x_in_place && op->own_n > 0) {  // local copy of src/vectors.jl:426-428, only when own columns have gaps
+        CU_TRY(launch_local_copy(op->csr->dtype, d_x, op->d_local_src, op->d_local_dst, op->own_n, op->d_gathered, stream));
+        op->launches += 1;
+    }
+    SpmvLaunch L;
+    fill_launch(op, L, d_x, d_y);
+    if (op->has_ghost) {  // interior tiles: only own columns, run while the halo is in flight
+        L.tile_list = op->d_list_int;
+        L.n_launch = op->n_int;
+    } else {
+        L.tile_list = nullptr;
+        L.n_launch = (int)op->csr->ntiles;
+    }
+    if (L.n_launch > 0) {
+        CU_TRY(launch_spmv_tiles(L, stream));
+        op->launches += 1;
+    }
+    if (!op->has_ghost) {
+        rc = launch_long(op, L, stream);
+        if (rc) return rc;
+    }
+    op->phase = 1;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
+    if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_finish: null");
+    if (op->phase != 1) return fail(HPCLA_ERR_STATE, "hpcla_spmv_finish: no multiply in flight");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    cudaStream_t stream = op->cur_stream;
+    if (op->has_peers) {
+        if (op->ctx->group) {
+            rc = exchange_finish_group(op);
+            if (rc) return rc;
+        }
+        // x (contiguous sends) and the packed buffer are read on the halo stream: the caller's stream must not run
+        // ahead of them, and the boundary tiles need the ghosts
+        CU_TRY(cudaStreamWaitEvent(stream, op->ev_halo, 0));
+        if (op->ctx->group) CU_TRY(cudaStreamWaitEvent(stream, op->ev_packed, 0));
+    }
+    if (op->has_ghost) {
+        SpmvLaunch L;
+        fill_launch(op, L, op->cur_x, op->cur_y);
+        L.tile_list = op->d_list_bnd;
+        L.n_launch = op->n_bnd;
+        if (L.n_launch > 0) {
+            CU_TRY(launch_spmv_tiles(L, stream));
+            op->launches += 1;
+        }
+        rc = launch_long(op, L, stream);
+        if (rc) return rc;
+    }
+    op->phase = 0;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* stream) {
+    if (op && op->ctx->group && op->ctx->nranks > 1 && op->has_peers)
+        return fail(HPCLA_ERR_STATE, "hpcla_spmv_run: in a single-process world call hpcla_spmv_begin on every rank, then hpcla_spmv_finish");
+    int rc = hpcla_spmv_begin(op, d_x, d_y, stream);
+    if (rc) return rc;
+    return hpcla_spmv_finish(op);
+}
+
+extern "C" int hpcla_spmv_gather(hpcla_spmv* op, const void* d_x, void* stream_, void** d_gathered_out) {
+    if (!op || !d_gathered_out) return fail(HPCLA_ERR_ARG, "hpcla_spmv_gather: null");
+    if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_gather: the previous call was not finished");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const hpcla_plan& P = op->plan;
+    const size_t es = dtype_size(op->csr->dtype);
+    if (!op->d_gathered) {
+        CU_TRY(cudaMalloc(&op->d_gathered, es * (size_t)std::max<i64>(P.n_gathered, 1)));
+        CU_TRY(cudaMemset(op->d_gathered, 0, es * (size_t)std::max<i64>(P.n_gathered, 1)));
+    }
+    if (!op->d_local_src && op->own_n > 0) {
+        CU_TRY(cudaMalloc(&op->d_local_src, sizeof(i64) * (size_t)op->own_n));
+        CU_TRY(cudaMalloc(&op->d_local_dst, sizeof(i64) * (size_t)op->own_n));
+        CU_TRY(cudaMemcpy(op->d_local_src, P.local_src.data(), sizeof(i64) * (size_t)op->own_n, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(op->d_local_dst, P.local_dst.data(), sizeof(i64) * (size_t)op->own_n, cudaMemcpyHostToDevice));
+    }
+    op->cur_x = d_x;
+    op->cur_stream = stream;
+    if (op->has_peers) {
+        rc = exchange_begin(op, d_x, stream);
+        if (rc) return rc;
+    }
+    if (op->own_n > 0) {
+        CU_TRY(launch_local_copy(op->csr->dtype, d_x, op->d_local_src, op->d_local_dst, op->own_n, op->d_gathered, stream));
+        op->launches += 1;
+    }
+    op->phase = 2;
+    *d_gathered_out = op->d_gathered;
+    if (!(op->ctx->group && op->ctx->nranks > 1 && op->has_peers)) return hpcla_spmv_gather_finish(op);
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_gather_finish(hpcla_spmv* op) {
+    if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_gather_finish: null");
+    if (op->phase == 0) return HPCLA_OK;  // already completed by hpcla_spmv_gather (NCCL world / single rank)
+    if (op->phase != 2) return fail(HPCLA_ERR_STATE, "hpcla_spmv_gather_finish: no gather in flight");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    if (op->has_peers) {
+        if (op->ctx->group) {
+            rc = exchange_finish_group(op);
+            if (rc) return rc;
+        }
+        CU_TRY(cudaStreamWaitEvent(op->cur_stream, op->ev_halo, 0));
+        if (op->ctx->group) CU_TRY(cudaStreamWaitEvent(op->cur_stream, op->ev_packed, 0));
+    }
+    op->phase = 0;
+    return HPCLA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reductions and updates
+// ---------------------------------------------------------------------------------------------------------------
+static int dot_to_host(hpcla_ctx* ctx, int dtype, i64 n, const void* d_x, const void* d_y, cudaStream_t stream, double out2[2]) {
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CU_TRY(launch_dot(dtype, n, d_x, d_y, ctx->d_red_scratch, ctx->d_red_out, stream));
+    if (ctx->comm && ctx->nranks > 1) NCCL_TRY(nccl_api()->AllReduce(ctx->d_red_out, ctx->d_red_out, 2, ncclFloat64, ncclSum, ctx->comm, stream));
+    CU_TRY(cudaMemcpyAsync(ctx->h_red_out, ctx->d_red_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    out2[0] = ctx->h_red_out[0];
+    out2[1] = ctx->h_red_out[1];
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_dot(hpcla_ctx* ctx, int dtype, int64_t n, const void* d_x, const void* d_y, void* result_out, void* stream) {
+    if (!ctx || !result_out || n < 0 || !dtype_size(dtype)) return fail(HPCLA_ERR_ARG, "hpcla_dot: bad arguments");
+    double r[2];
+    int rc = dot_to_host(ctx, dtype, n, d_x, d_y, (cudaStream_t)stream, r);
+    if (rc) return rc;
+    if (dtype == HPCLA_F32) *(float*)result_out = (float)r[0];
+    else if (dtype == HPCLA_F64) *(double*)result_out = r[0];
+    else ((double*)result_out)[0] = r[0], ((double*)result_out)[1] = r[1];
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_nrm2(hpcla_ctx* ctx, int dtype, int64_t n, const void* d_x, void* result_out, void* stream) {
+    if (!ctx || !result_out || n < 0 || !dtype_size(dtype)) return fail(HPCLA_ERR_ARG, "hpcla_nrm2: bad arguments");
+    double r[2];
+    int rc = dot_to_host(ctx, dtype, n, d_x, d_x, (cudaStream_t)stream, r);
+    if (rc) return rc;
+    const double v = ctx->group && ctx->nranks > 1 ? r[0] : std::sqrt(r[0]);
+    if (dtype == HPCLA_F32) *(float*)result_out = (float)v;
+    else *(double*)result_out = v;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_axpby(hpcla_ctx* ctx, int dtype, int64_t n, const void* alpha, const void* d_x, const void* beta, void* d_y, void* stream) {
+    if (!ctx || !alpha || !beta || n < 0 || !dtype_size(dtype)) return fail(HPCLA_ERR_ARG, "hpcla_axpby: bad arguments");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CU_TRY(launch_axpby(dtype, n, alpha, d_x, beta, d_y, (cudaStream_t)stream));
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work, int iters, double* rr_history_out, void* stream_) {
+    if (!op || !d_b || !d_x || !d_work || iters < 0) return fail(HPCLA_ERR_ARG, "hpcla_cg: bad arguments");
+    hpcla_ctx* ctx = op->ctx;
+    const int dtype = op->csr->dtype;
+    if (dtype == HPCLA_C128) return fail(HPCLA_ERR_ARG, "hpcla_cg: real element types only");
+    if (ctx->group && ctx->nranks > 1) return fail(HPCLA_ERR_STATE, "hpcla_cg: needs an NCCL world or a single rank");
+    if (op->csr->nrows != op->n_x_local) return fail(HPCLA_ERR_ARG, "hpcla_cg: A must be square with x partitioned like its rows");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const i64 n = op->csr->nrows;
+    const size_t es = dtype_size(dtype);
+    char* r = (char*)d_work;
+    char* p = r + (size_t)n * es;
+    char* q = p + (size_t)n * es;
+    double* d_s = nullptr;  // rr_k at [2k], pq at the tail
+    CU_TRY(cudaMalloc(&d_s, sizeof(double) * (size_t)(2 * (iters + 1) + 2)));
+    double* d_pq = d_s + 2 * (iters + 1);
+    const bool multi = ctx->comm && ctx->nranks > 1;
+    NcclApi* api = multi ? nccl_api() : nullptr;
+    CU_TRY(launch_cg_init(dtype, n, d_b, d_x, r, p, ctx->d_red_scratch, d_s, stream));
+    if (multi) NCCL_TRY(api->AllReduce(d_s, d_s, 1, ncclFloat64, ncclSum, ctx->comm, stream));
+    for (int k = 0; k < iters; ++k) {
+        rc = hpcla_spmv_run(op, p, q, stream);
+        if (rc) { cudaFree(d_s); return rc; }
+        CU_TRY(launch_dot(dtype, n, p, q, ctx->d_red_scratch, d_pq, stream));
+        if (multi) NCCL_TRY(api->AllReduce(d_pq, d_pq, 1, ncclFloat64, ncclSum, ctx->comm, stream));
+        CU_TRY(launch_cg_update_xr(dtype, n, p, q, d_x, r, d_s + 2 * k, d_pq, ctx->d_red_scratch, d_s + 2 * (k + 1), stream));
+        if (multi) NCCL_TRY(api->AllReduce(d_s + 2 * (k + 1), d_s + 2 * (k + 1), 1, ncclFloat64, ncclSum, ctx->comm, stream));
+        CU_TRY(launch_cg_update_p(dtype, n, r, p, d_s + 2 * (k + 1), d_s + 2 * k, stream));
+    }
+    std::vector<double> h((size_t)(2 * (iters + 1)));
+    CU_TRY(cudaMemcpyAsync(h.data(), d_s, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    cudaFree(d_s);
+    if (rr_history_out)
+        for (int k = 0; k < iters; ++k) rr_history_out[k] = h[(size_t)(2 * (k + 1))];
+    return HPCLA_OK;
+}

@@ -1,0 +1,89 @@
+// device.h — internal interface between the orchestration (context.cu) and the kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.h"
+
+namespace hpcla {
+
+// One row tile: rows [row, next.row) whose first stored entry lies in one window of the nonzero stream;
+// nnz = 0-based offset of the first stored entry of `row`.
+struct TileDesc {
+    i64 row;
+    i64 nnz;
+};
+
+// Tunables of the tile kernel for one element type (see kernels.cu).
+struct TileShape {
+    int threads;     // CTA size
+    int chunk;       // nonzeros staged per round = threads * groups * 4
+    int window;      // nonzeros per tile window = chunk - 64
+    int smem_elems;  // products that fit in shared memory = chunk + 512
+};
+TileShape tile_shape(int dtype);
+
+struct SpmvLaunch {
+    int dtype, itype;
+    const void* rowptr;
+    const void* colval;
+    const void* nzval;
+    i64 nrows, nnz;
+    const TileDesc* tiles;  // [ntiles+1]
+    const int* tile_list;   // nullptr: tiles 0..n_launch-1
+    int n_launch;
+    // x addressing for a 1-based compressed column c:
+    //   own  <=> own_lo <= c < own_lo + own_n           -> x_own[c - own_lo]   (x_own already offset to the first own source)
+    //   else                                            -> gathered[c - 1]
+    const void* x_own;
+    const void* gathered;
+    i64 own_lo, own_n;
+    bool has_ghost;  // false: every column is own (single rank, or no off-rank columns)
+    void* y;
+    i64 long_threshold;  // rows longer than this are left to the split kernels
+};
+
+cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles,
+                               cudaStream_t st);
+// rows longer than threshold: writes their local row ids (ascending not guaranteed) into rows_out (capacity cap), count via *count_out (device)
+cudaError_t launch_find_long_rows(int itype, const void* rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
+                                  unsigned long long* count_out, cudaStream_t st);
+// flags[t] = 1 iff tile t references a column outside [own_lo, own_lo+own_n)
+cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n,
+                                  unsigned char* flags, cudaStream_t st);
+cudaError_t launch_spmv_tiles(const SpmvLaunch& L, cudaStream_t st);
+
+struct LongRowsLaunch {
+    int dtype, itype;
+    const void* rowptr;
+    const void* colval;
+    const void* nzval;
+    const i64* long_rows;   // [nlong] local row ids
+    const i64* chunk_ptr;   // [nlong+1] prefix of chunk counts
+    i64 nlong, nchunks, chunk_nnz;
+    const void* x_own;
+    const void* gathered;
+    i64 own_lo, own_n;
+    bool has_ghost;
+    void* partials;  // T[nchunks]
+    void* y;
+};
+cudaError_t launch_long_rows(const LongRowsLaunch& L, cudaStream_t st);
+
+// out[k] = x[idx[k]-1]          (pack of src/vectors.jl:431-437, all peers in one launch)
+cudaError_t launch_pack(int dtype, const void* x, const i64* idx, i64 n, void* out, cudaStream_t st);
+// gathered[dst[k]-1] = x[src[k]-1]   (local copy of src/vectors.jl:426-428 == _gather_kernel! :174-177)
+cudaError_t launch_local_copy(int dtype, const void* x, const i64* src, const i64* dst, i64 n, void* gathered, cudaStream_t st);
+
+// reductions / updates.  scratch: device buffer of >= reduce_scratch_elems() doubles.
+int reduce_scratch_doubles();
+// out2[0..1] (double, device) = sum conj(x)*y (re, im); F32 accumulates in float per thread, double across threads
+cudaError_t launch_dot(int dtype, i64 n, const void* x, const void* y, double* scratch, double* out2, cudaStream_t st);
+cudaError_t launch_axpby(int dtype, i64 n, const void* alpha_host, const void* x, const void* beta_host, void* y, cudaStream_t st);
+
+// CG building blocks (real types).  All scalars are (re, im) double pairs on the device.
+cudaError_t launch_cg_init(int dtype, i64 n, const void* b, void* x, void* r, void* p, double* scratch, double* rr_out2, cudaStream_t st);
+cudaError_t launch_cg_update_xr(int dtype, i64 n, const void* p, const void* q, void* x, void* r, const double* rr, const double* pq,
+                                double* scratch, double* rr_new_out2, cudaStream_t st);
+cudaError_t launch_cg_update_p(int dtype, i64 n, const void* r, void* p, const double* rr_new, const double* rr, cudaStream_t st);
+
+}  // namespace hpcla

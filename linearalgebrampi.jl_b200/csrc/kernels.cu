@@ -1,0 +1,670 @@
+// kernels.cu — hand-written sm_100a kernels of the distributed SpMV hot path.
+//
+// The arithmetic replaces the reference's one-work-item-per-row KernelAbstractions kernel
+// (_spmv_kernel!, src/sparse.jl:2055-2066) and its gather kernel (_gather_kernel!, src/vectors.jl:174-177).
+// SpMV is HBM-bound (0.10-0.37 flop/B): no tensor cores; the design goals are
+//   * every byte of nzval / colval read exactly once with 128-bit, fully coalesced, streaming (evict-first) loads:
+//     consecutive NONZEROS (not rows) are assigned to consecutive lanes;
+//   * x read through the read-only path (L1/L2 resident for stencil-like column locality);
+//   * products staged in shared memory, then reduced per row by 1, 2, 4, ... 32 lanes chosen per tile from the
+//     mean row length (thread- / sub-warp- / warp-per-row), a warp-per-row streaming path for tiles whose rows do
+//     not fit, and a split (chunk + ordered partial sums, no atomics) path for very long power-law rows;
+//   * the reference's 1-based Int32/Int64 arrays are consumed as they are (no conversion pass, no private copy).
+// With one lane per row the per-row sum runs left to right over products rounded separately from the adds, i.e.
+// bit-identical to the reference's `acc += nzval[j]*x[colval[j]]` (no FMA contraction) for rows of <= 12 entries.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device.h"
+
+namespace hpcla {
+
+// ------------------------------------------------------------------------------------------------------------------
+// element-type helpers
+// ------------------------------------------------------------------------------------------------------------------
+struct cplx {
+    double re, im;
+};
+
+__device__ __forceinline__ float el_zero(float) { return 0.f; }
+__device__ __forceinline__ double el_zero(double) { return 0.0; }
+__device__ __forceinline__ cplx el_zero(cplx) { return cplx{0.0, 0.0}; }
+// products are rounded on their own (__fmul_rn/__dmul_rn are never contracted into an FMA)
+__device__ __forceinline__ float el_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double el_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ cplx el_mul(cplx a, cplx b) {
+    return cplx{__dsub_rn(__dmul_rn(a.re, b.re), __dmul_rn(a.im, b.im)), __dadd_rn(__dmul_rn(a.re, b.im), __dmul_rn(a.im, b.re))};
+}
+__device__ __forceinline__ float el_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double el_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ cplx el_add(cplx a, cplx b) { return cplx{__dadd_rn(a.re, b.re), __dadd_rn(a.im, b.im)}; }
+
+__device__ __forceinline__ float shfl_xor(float v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ cplx shfl_xor(cplx v, int m) {
+    return cplx{__shfl_xor_sync(0xffffffffu, v.re, m), __shfl_xor_sync(0xffffffffu, v.im, m)};
+}
+
+// read-only-path scalar loads of x
+__device__ __forceinline__ float ld_x(const float* p) { return __ldg(p); }
+__device__ __forceinline__ double ld_x(const double* p) { return __ldg(p); }
+__device__ __forceinline__ cplx ld_x(const cplx* p) {
+    double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    return cplx{t.x, t.y};
+}
+// streaming (evict-first) scalar loads of the matrix, for the unaligned / tail cases
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ cplx ld_stream(const cplx* p) {
+    double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+    return cplx{t.x, t.y};
+}
+__device__ __forceinline__ int ld_stream(const int* p) { return __ldcs(p); }
+__device__ __forceinline__ long long ld_stream(const long long* p) { return __ldcs(p); }
+
+// 4 consecutive elements from a 16-byte aligned address, 128-bit streaming loads
+__device__ __forceinline__ void ld4_stream(const float* p, float (&v)[4]) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void ld4_stream(const double* p, double (&v)[4]) {
+    double2 a = __ldcs(reinterpret_cast<const double2*>(p));
+    double2 b = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+__device__ __forceinline__ void ld4_stream(const cplx* p, cplx (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double2 t = __ldcs(reinterpret_cast<const double2*>(p) + k);
+        v[k] = cplx{t.x, t.y};
+    }
+}
+__device__ __forceinline__ void ld4_stream(const int* p, int (&v)[4]) {
+    int4 t = __ldcs(reinterpret_cast<const int4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void ld4_stream(const long long* p, long long (&v)[4]) {
+    longlong2 a = __ldcs(reinterpret_cast<const longlong2*>(p));
+    longlong2 b = __ldcs(reinterpret_cast<const longlong2*>(p) + 1);
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+// 4 consecutive products to a 16-byte aligned shared address
+__device__ __forceinline__ void st4_shared(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void st4_shared(double* p, const double (&v)[4]) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+}
+__device__ __forceinline__ void st4_shared(cplx* p, const cplx (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) reinterpret_cast<double2*>(p)[k] = make_double2(v[k].re, v[k].im);
+}
+__device__ __forceinline__ void st_y(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_y(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_y(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
+
+// x addressing: own columns are read straight from x.v (no local copy into `gathered`), ghosts from `gathered`.
+template <class T>
+struct XView {
+    const T* own;  // own[c] valid for own_lo <= c < own_lo + own_n   (pointer pre-shifted by -own_lo)
+    const T* gat;  // gat[c] == gathered[c-1]                           (pointer pre-shifted by -1)
+    i64 own_lo;
+    unsigned long long own_n;
+};
+template <bool GHOST, class T, class Ti>
+__device__ __forceinline__ T x_at(const XView<T>& xv, Ti c) {
+    if (GHOST) {
+        const T* p = ((unsigned long long)((i64)c - xv.own_lo) < xv.own_n) ? xv.own : xv.gat;
+        return ld_x(p + (i64)c);
+    }
+    return ld_x(xv.own + (i64)c);
+}
+
+template <class T, class Ti>
+struct TileArgs {
+    const Ti* rowptr;
+    const Ti* colval;
+    const T* nzval;
+    XView<T> xv;
+    T* y;
+    const TileDesc* tiles;
+    const int* tile_list;
+    i64 nnz_total;
+    i64 long_threshold;
+    i64 safe_col;  // a column that is always valid to read (padding lanes)
+};
+
+// per-row reduction of staged products by G cooperating lanes (G = 1: the reference's left-to-right order)
+template <class T, class Ti, int THREADS, int G>
+__device__ __forceinline__ void reduce_rows(const T* prod, const Ti* __restrict__ rowptr, T* __restrict__ y, i64 r0, i64 r1, i64 s4,
+                                            int tid) {
+    constexpr int RPP = THREADS / G;  // rows per pass
+    const int lane = tid % G;
+    for (i64 base = r0; base < r1; base += RPP) {
+        const i64 r = base + tid / G;
+        const bool valid = r < r1;
+        T acc = el_zero(T());
+        if (valid) {
+            const int b = (int)((i64)__ldg(rowptr + r) - 1 - s4);
+            const int e = (int)((i64)__ldg(rowptr + r + 1) - 1 - s4);
+            for (int k = b + lane; k < e; k += G) acc = el_add(acc, prod[k]);
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+        }
+        if (valid && lane == 0) st_y(y + r, acc);
+    }
+}
+
+template <class T, class Ti, int THREADS, int GROUPS, bool GHOST>
+__global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti> a, int smem_elems) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* prod = reinterpret_cast<T*>(smem_raw);
+    constexpr int CHUNK = THREADS * GROUPS * 4;
+    const int tid = threadIdx.x;
+    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
+    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
+    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
+    const i64 r0 = d0.x, r1 = d1.x;
+    if (r1 <= r0) return;
+    const i64 s = d0.y, e = d1.y;  // 0-based nonzero range of the tile
+    const i64 s4 = s & ~(i64)3;    // 16-byte aligned start for every element width
+    const i64 n = e - s4;
+
+    if (n <= (i64)smem_elems) {
+        // ---- stage: coalesced 128-bit streaming loads of 4 consecutive nonzeros per lane, gather x, multiply ----
+        const Ti* __restrict__ cb = a.colval + s4;
+        const T* __restrict__ vb = a.nzval + s4;
+        const i64 avail = a.nnz_total - s4;  // elements that exist from s4 on
+        for (int base = 0; base < (int)n; base += CHUNK) {
+            Ti c[GROUPS][4];
+            T v[GROUPS][4];
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                const int i = base + (g * THREADS + tid) * 4;
+                if (i + 4 <= avail && i < n) {
+                    ld4_stream(cb + i, c[g]);
+                    ld4_stream(vb + i, v[g]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool ok = (i + k < avail) && (i + k < n);
+                        c[g][k] = ok ? ld_stream(cb + i + k) : (Ti)a.safe_col;
+                        v[g][k] = ok ? ld_stream(vb + i + k) : el_zero(T());
+                    }
+                }
+            }
+            T xg[GROUPS][4];
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xg[g][k] = x_at<GHOST, T, Ti>(a.xv, c[g][k]);
+#pragma unroll
+            for (int g = 0; g < GROUPS; ++g) {
+                const int i = base + (g * THREADS + tid) * 4;
+                if (i < n) {
+                    T p[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) p[k] = el_mul(v[g][k], xg[g][k]);
+                    st4_shared(prod + i, p);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- reduce: lanes per row from the tile's mean row length (warp-uniform) ----
+        const i64 nrows_t = r1 - r0;
+        const i64 avg = (e - s) / nrows_t;
+        if (avg <= 12) reduce_rows<T, Ti, THREADS, 1>(prod, a.rowptr, a.y, r0, r1, s4, tid);
+        else if (avg <= 24) reduce_rows<T, Ti, THREADS, 2>(prod, a.rowptr, a.y, r0, r1, s4, tid);
+        else if (avg <= 48) reduce_rows<T, Ti, THREADS, 4>(prod, a.rowptr, a.y, r0, r1, s4, tid);
+        else if (avg <= 96) reduce_rows<T, Ti, THREADS, 8>(prod, a.rowptr, a.y, r0, r1, s4, tid);
+        else if (avg <= 192) reduce_rows<T, Ti, THREADS, 16>(prod, a.rowptr, a.y, r0, r1, s4, tid);
+        else reduce_rows<T, Ti, THREADS, 32>(prod, a.rowptr, a.y, r0, r1, s4, tid);
+    } else {
+        // ---- the tile holds a row too long to stage: warp-per-row straight from global memory ----
+        const int warp = tid >> 5, lane = tid & 31;
+        for (i64 r = r0 + warp; r < r1; r += THREADS / 32) {
+            const i64 b = (i64)__ldg(a.rowptr + r) - 1, en = (i64)__ldg(a.rowptr + r + 1) - 1;
+            if (en - b > a.long_threshold) continue;  // left to the split kernels
+            T acc = el_zero(T());
+            for (i64 k = b + lane; k < en; k += 32) {
+                const Ti c = ld_stream(a.colval + k);
+                acc = el_add(acc, el_mul(ld_stream(a.nzval + k), x_at<GHOST, T, Ti>(a.xv, c)));
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+            if (lane == 0) st_y(a.y + r, acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// very long rows ("merge-path split"): the row's nonzero range is cut into equal chunks, one CTA per chunk writes
+// one partial sum, a second kernel adds the partials of a row in chunk order.  Deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ T block_sum(T v, T* sh /* [32] */) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = el_add(v, shfl_xor(v, m));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    T r = el_zero(T());
+    if (warp == 0) {
+        r = lane < (int)(blockDim.x >> 5) ? sh[lane] : el_zero(T());
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) r = el_add(r, shfl_xor(r, m));
+    }
+    return r;  // valid in warp 0
+}
+
+template <class T, class Ti, bool GHOST>
+__global__ void __launch_bounds__(256) long_rows_partial_kernel(const Ti* __restrict__ rowptr, const Ti* __restrict__ colval,
+                                                                const T* __restrict__ nzval, const i64* __restrict__ long_rows,
+                                                                const i64* __restrict__ chunk_ptr, i64 nlong, i64 chunk_nnz, XView<T> xv,
+                                                                T* __restrict__ partials) {
+    __shared__ T sh[32];
+    const i64 chunk = blockIdx.x;
+    i64 lo = 0, hi = nlong;  // last i with chunk_ptr[i] <= chunk
+    while (hi - lo > 1) {
+        const i64 mid = (lo + hi) >> 1;
+        if (chunk_ptr[mid] <= chunk) lo = mid;
+        else hi = mid;
+    }
+    const i64 r = long_rows[lo];
+    const i64 rb = (i64)rowptr[r] - 1, re = (i64)rowptr[r + 1] - 1;
+    const i64 b = rb + (chunk - chunk_ptr[lo]) * chunk_nnz;
+    const i64 e = (b + chunk_nnz < re) ? b + chunk_nnz : re;
+    T acc0 = el_zero(T()), acc1 = el_zero(T());
+    i64 k = b + threadIdx.x;
+    for (; k + 256 < e; k += 512) {
+        const Ti c0 = ld_stream(colval + k), c1 = ld_stream(colval + k + 256);
+        const T v0 = ld_stream(nzval + k), v1 = ld_stream(nzval + k + 256);
+        acc0 = el_add(acc0, el_mul(v0, x_at<GHOST, T, Ti>(xv, c0)));
+        acc1 = el_add(acc1, el_mul(v1, x_at<GHOST, T, Ti>(xv, c1)));
+    }
+    if (k < e) acc0 = el_add(acc0, el_mul(ld_stream(nzval + k), x_at<GHOST, T, Ti>(xv, ld_stream(colval + k))));
+    T tot = block_sum(el_add(acc0, acc1), sh);
+    if (threadIdx.x == 0) partials[chunk] = tot;
+}
+
+template <class T>
+__global__ void long_rows_final_kernel(const i64* __restrict__ long_rows, const i64* __restrict__ chunk_ptr, i64 nlong,
+                                       const T* __restrict__ partials, T* __restrict__ y) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlong) return;
+    T acc = el_zero(T());
+    for (i64 c = chunk_ptr[i]; c < chunk_ptr[i + 1]; ++c) acc = el_add(acc, partials[c]);
+    y[long_rows[i]] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// structure kernels (run once per handle / plan)
+// ------------------------------------------------------------------------------------------------------------------
+template <class Ti>
+__global__ void build_tiles_kernel(const Ti* __restrict__ rowptr, i64 nrows, int window, TileDesc* tiles, i64 ntiles) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > ntiles) return;
+    i64 r;
+    if (k == ntiles) r = nrows;
+    else {
+        const i64 target = k * (i64)window;  // first row whose first stored entry is at or after `target`
+        i64 lo = 0, hi = nrows + 1;
+        while (lo < hi) {
+            const i64 mid = (lo + hi) >> 1;
+            if ((i64)rowptr[mid] - 1 < target) lo = mid + 1;
+            else hi = mid;
+        }
+        r = lo > nrows ? nrows : lo;
+    }
+    tiles[k].row = r;
+    tiles[k].nnz = (i64)rowptr[r] - 1;
+}
+
+template <class Ti>
+__global__ void find_long_rows_kernel(const Ti* __restrict__ rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
+                                      unsigned long long* count) {
+    const i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    if ((i64)rowptr[r + 1] - (i64)rowptr[r] > threshold) {
+        const unsigned long long slot = atomicAdd(count, 1ull);
+        if ((i64)slot < cap) rows_out[slot] = r;
+    }
+}
+
+template <class Ti>
+__global__ void __launch_bounds__(256) classify_tiles_kernel(const Ti* __restrict__ colval, const TileDesc* __restrict__ tiles, i64 own_lo,
+                                                             unsigned long long own_n, unsigned char* flags) {
+    const i64 t = blockIdx.x;
+    const i64 b = tiles[t].nnz, e = tiles[t + 1].nnz;
+    int ghost = 0;
+    for (i64 k = b + threadIdx.x; k < e; k += 256) ghost |= ((unsigned long long)((i64)colval[k] - own_lo) >= own_n);
+    ghost = __syncthreads_or(ghost);
+    if (threadIdx.x == 0) flags[t] = ghost ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// halo pack / local copy
+// ------------------------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void pack_kernel(const T* __restrict__ x, const i64* __restrict__ idx, i64 n, T* __restrict__ out) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = x[idx[k] - 1];
+}
+template <class T>
+__global__ void local_copy_kernel(const T* __restrict__ x, const i64* __restrict__ src, const i64* __restrict__ dst, i64 n, T* __restrict__ g) {
+    const i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) g[dst[k] - 1] = x[src[k] - 1];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// reductions and vector updates (HPCVector dot / norm / broadcast, src/vectors.jl:758-812, 1203-1221)
+// Two-level deterministic sum: per-CTA partials, the last CTA to finish adds them in index order.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 148 * 8;
+
+struct d2 {
+    double re, im;
+};
+__device__ __forceinline__ void acc_dot(d2& a, float x, float y) { a.re += (double)x * (double)y; }
+__device__ __forceinline__ void acc_dot(d2& a, double x, double y) { a.re += x * y; }
+__device__ __forceinline__ void acc_dot(d2& a, cplx x, cplx y) {  // conj(x) * y
+    a.re += x.re * y.re + x.im * y.im;
+    a.im += x.re * y.im - x.im * y.re;
+}
+
+// scratch layout: [0 .. 2*RED_MAX_BLOCKS) partial (re, im) pairs, then one unsigned counter (as a double slot)
+__device__ __forceinline__ void finish_reduction(d2 mine, double* scratch, double* out2) {
+    __shared__ double shre[32], shim[32];
+    __shared__ bool is_last;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        mine.re += __shfl_xor_sync(0xffffffffu, mine.re, m);
+        mine.im += __shfl_xor_sync(0xffffffffu, mine.im, m);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) shre[warp] = mine.re, shim[warp] = mine.im;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double re = 0, im = 0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) re += shre[w], im += shim[w];
+        scratch[2 * blockIdx.x] = re;
+        scratch[2 * blockIdx.x + 1] = im;
+        __threadfence();
+        unsigned* counter = reinterpret_cast<unsigned*>(scratch + 2 * RED_MAX_BLOCKS);
+        const unsigned done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double re = 0, im = 0;  // fixed order: thread t takes partials t, t+256, ...; then the same tree as above
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += RED_THREADS) {
+            re += __ldcg(scratch + 2 * b);
+            im += __ldcg(scratch + 2 * b + 1);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, m);
+            im += __shfl_xor_sync(0xffffffffu, im, m);
+        }
+        __syncthreads();
+        if (lane == 0) shre[warp] = re, shim[warp] = im;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double r2 = 0, i2 = 0;
+            for (int w = 0; w < RED_THREADS / 32; ++w) r2 += shre[w], i2 += shim[w];
+            out2[0] = r2;
+            out2[1] = i2;
+            *reinterpret_cast<unsigned*>(scratch + 2 * RED_MAX_BLOCKS) = 0u;  // re-arm
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(RED_THREADS) dot_kernel(i64 n, const T* __restrict__ x, const T* __restrict__ y, double* scratch, double* out2) {
+    d2 a{0.0, 0.0};
+    for (i64 i = (i64)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * RED_THREADS) acc_dot(a, ld_x(x + i), ld_x(y + i));
+    finish_reduction(a, scratch, out2);
+}
+
+template <class T>
+struct Scal {
+    T v;
+};
+__device__ __forceinline__ float axpby1(float a, float x, float b, float y) { return a * x + b * y; }
+__device__ __forceinline__ double axpby1(double a, double x, double b, double y) { return a * x + b * y; }
+__device__ __forceinline__ cplx axpby1(cplx a, cplx x, cplx b, cplx y) { return el_add(el_mul(a, x), el_mul(b, y)); }
+template <class T>
+__global__ void axpby_kernel(i64 n, Scal<T> alpha, const T* __restrict__ x, Scal<T> beta, T* __restrict__ y) {
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) y[i] = axpby1(alpha.v, x[i], beta.v, y[i]);
+}
+
+// CG: r = b, p = b, x = 0, rr = dot(b, b)
+template <class T>
+__global__ void __launch_bounds__(RED_THREADS) cg_init_kernel(i64 n, const T* __restrict__ b, T* __restrict__ x, T* __restrict__ r, T* __restrict__ p,
+                                                              double* scratch, double* rr_out2) {
+    d2 a{0.0, 0.0};
+    for (i64 i = (i64)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * RED_THREADS) {
+        const T bi = b[i];
+        x[i] = (T)0;
+        r[i] = bi;
+        p[i] = bi;
+        acc_dot(a, bi, bi);
+    }
+    finish_reduction(a, scratch, rr_out2);
+}
+// alpha = rr/pq ; x += alpha p ; r -= alpha q ; rr_new = dot(r, r)
+template <class T>
+__global__ void __launch_bounds__(RED_THREADS) cg_update_xr_kernel(i64 n, const T* __restrict__ p, const T* __restrict__ q, T* __restrict__ x,
+                                                                   T* __restrict__ r, const double* __restrict__ rr, const double* __restrict__ pq,
+                                                                   double* scratch, double* rr_new_out2) {
+    const T alpha = (T)(rr[0] / pq[0]);
+    d2 a{0.0, 0.0};
+    for (i64 i = (i64)blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * RED_THREADS) {
+        x[i] = x[i] + alpha * p[i];
+        const T ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        acc_dot(a, ri, ri);
+    }
+    finish_reduction(a, scratch, rr_new_out2);
+}
+// beta = rr_new/rr ; p = r + beta p
+template <class T>
+__global__ void cg_update_p_kernel(i64 n, const T* __restrict__ r, T* __restrict__ p, const double* __restrict__ rr_new, const double* __restrict__ rr) {
+    const T beta = (T)(rr_new[0] / rr[0]);
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64)gridDim.x * blockDim.x) p[i] = r[i] + beta * p[i];
+}
+
+// ==================================================================================================================
+// host-side launchers
+// ==================================================================================================================
+template <class T> struct TileCfg;
+template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2; };
+template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2; };
+template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1; };
+
+template <class T>
+static TileShape shape_of() {
+    TileShape s;
+    s.threads = TileCfg<T>::THREADS;
+    s.chunk = TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4;
+    s.window = s.chunk - 64;
+    s.smem_elems = s.chunk + 512;
+    return s;
+}
+TileShape tile_shape(int dtype) {
+    if (dtype == HPCLA_F32) return shape_of<float>();
+    if (dtype == HPCLA_F64) return shape_of<double>();
+    return shape_of<cplx>();
+}
+
+static inline int blocks_for(i64 n, int threads) { return (int)((n + threads - 1) / threads); }
+
+cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles, cudaStream_t st) {
+    (void)nnz;
+    const int blocks = blocks_for(ntiles + 1, 256);
+    if (itype == HPCLA_I32) build_tiles_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, nrows, window, tiles, ntiles);
+    else build_tiles_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, nrows, window, tiles, ntiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_find_long_rows(int itype, const void* rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap, unsigned long long* count_out,
+                                  cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    const int blocks = blocks_for(nrows, 256);
+    if (itype == HPCLA_I32) find_long_rows_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, nrows, threshold, rows_out, cap, count_out);
+    else find_long_rows_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, nrows, threshold, rows_out, cap, count_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n, unsigned char* flags,
+                                  cudaStream_t st) {
+    if (ntiles == 0) return cudaSuccess;
+    if (itype == HPCLA_I32) classify_tiles_kernel<int><<<(unsigned)ntiles, 256, 0, st>>>((const int*)colval, tiles, own_lo, (unsigned long long)own_n, flags);
+    else classify_tiles_kernel<long long><<<(unsigned)ntiles, 256, 0, st>>>((const long long*)colval, tiles, own_lo, (unsigned long long)own_n, flags);
+    return cudaGetLastError();
+}
+
+template <class T>
+static XView<T> make_xview(const void* x_own, const void* gathered, i64 own_lo, i64 own_n) {
+    XView<T> v;
+    v.own = x_own ? (const T*)x_own - own_lo : nullptr;
+    v.gat = gathered ? (const T*)gathered - 1 : nullptr;
+    v.own_lo = own_lo;
+    v.own_n = (unsigned long long)own_n;
+    return v;
+}
+
+template <class T, class Ti>
+static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
+    if (L.n_launch <= 0) return cudaSuccess;
+    constexpr int THREADS = TileCfg<T>::THREADS, GROUPS = TileCfg<T>::GROUPS;
+    const TileShape sh = shape_of<T>();
+    TileArgs<T, Ti> a;
+    a.rowptr = (const Ti*)L.rowptr;
+    a.colval = (const Ti*)L.colval;
+    a.nzval = (const T*)L.nzval;
+    a.xv = make_xview<T>(L.x_own, L.gathered, L.own_lo, L.own_n);
+    a.y = (T*)L.y;
+    a.tiles = L.tiles;
+    a.tile_list = L.tile_list;
+    a.nnz_total = L.nnz;
+    a.long_threshold = L.long_threshold;
+    a.safe_col = L.own_n > 0 ? L.own_lo : 1;
+    const size_t smem = (size_t)sh.smem_elems * sizeof(T);
+    if (L.has_ghost) spmv_tile_kernel<T, Ti, THREADS, GROUPS, true><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
+    else spmv_tile_kernel<T, Ti, THREADS, GROUPS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
+    return cudaGetLastError();
+}
+
+#define HPCLA_DISPATCH(FN, L, ...)                                                                     \
+    do {                                                                                               \
+        if ((L).dtype == HPCLA_F32 && (L).itype == HPCLA_I32) return FN<float, int>(__VA_ARGS__);       \
+        if ((L).dtype == HPCLA_F32 && (L).itype == HPCLA_I64) return FN<float, long long>(__VA_ARGS__); \
+        if ((L).dtype == HPCLA_F64 && (L).itype == HPCLA_I32) return FN<double, int>(__VA_ARGS__);      \
+        if ((L).dtype == HPCLA_F64 && (L).itype == HPCLA_I64) return FN<double, long long>(__VA_ARGS__);\
+        if ((L).dtype == HPCLA_C128 && (L).itype == HPCLA_I32) return FN<cplx, int>(__VA_ARGS__);       \
+        if ((L).dtype == HPCLA_C128 && (L).itype == HPCLA_I64) return FN<cplx, long long>(__VA_ARGS__); \
+        return cudaErrorInvalidValue;                                                                  \
+    } while (0)
+
+cudaError_t launch_spmv_tiles(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_tiles_typed, L, L, st); }
+
+template <class T, class Ti>
+static cudaError_t long_rows_typed(const LongRowsLaunch& L, cudaStream_t st) {
+    if (L.nlong == 0) return cudaSuccess;
+    XView<T> xv = make_xview<T>(L.x_own, L.gathered, L.own_lo, L.own_n);
+    if (L.has_ghost)
+        long_rows_partial_kernel<T, Ti, true><<<(unsigned)L.nchunks, 256, 0, st>>>((const Ti*)L.rowptr, (const Ti*)L.colval, (const T*)L.nzval, L.long_rows,
+                                                                                  L.chunk_ptr, L.nlong, L.chunk_nnz, xv, (T*)L.partials);
+    else
+        long_rows_partial_kernel<T, Ti, false><<<(unsigned)L.nchunks, 256, 0, st>>>((const Ti*)L.rowptr, (const Ti*)L.colval, (const T*)L.nzval, L.long_rows,
+                                                                                   L.chunk_ptr, L.nlong, L.chunk_nnz, xv, (T*)L.partials);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    long_rows_final_kernel<T><<<blocks_for(L.nlong, 128), 128, 0, st>>>(L.long_rows, L.chunk_ptr, L.nlong, (const T*)L.partials, (T*)L.y);
+    return cudaGetLastError();
+}
+cudaError_t launch_long_rows(const LongRowsLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(long_rows_typed, L, L, st); }
+
+#define HPCLA_DISPATCH_T(dtype, CALL_F32, CALL_F64, CALL_C128) \
+    do {                                                       \
+        if ((dtype) == HPCLA_F32) { CALL_F32; }                \
+        else if ((dtype) == HPCLA_F64) { CALL_F64; }           \
+        else if ((dtype) == HPCLA_C128) { CALL_C128; }         \
+        else return cudaErrorInvalidValue;                     \
+    } while (0)
+
+cudaError_t launch_pack(int dtype, const void* x, const i64* idx, i64 n, void* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int b = blocks_for(n, 256);
+    HPCLA_DISPATCH_T(dtype, (pack_kernel<float><<<b, 256, 0, st>>>((const float*)x, idx, n, (float*)out)),
+                     (pack_kernel<double><<<b, 256, 0, st>>>((const double*)x, idx, n, (double*)out)),
+                     (pack_kernel<double2><<<b, 256, 0, st>>>((const double2*)x, idx, n, (double2*)out)));
+    return cudaGetLastError();
+}
+cudaError_t launch_local_copy(int dtype, const void* x, const i64* src, const i64* dst, i64 n, void* g, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int b = blocks_for(n, 256);
+    HPCLA_DISPATCH_T(dtype, (local_copy_kernel<float><<<b, 256, 0, st>>>((const float*)x, src, dst, n, (float*)g)),
+                     (local_copy_kernel<double><<<b, 256, 0, st>>>((const double*)x, src, dst, n, (double*)g)),
+                     (local_copy_kernel<double2><<<b, 256, 0, st>>>((const double2*)x, src, dst, n, (double2*)g)));
+    return cudaGetLastError();
+}
+
+int reduce_scratch_doubles() { return 2 * RED_MAX_BLOCKS + 2; }
+static inline int red_blocks(i64 n) {
+    i64 b = (n + RED_THREADS * 4 - 1) / (RED_THREADS * 4);
+    if (b < 1) b = 1;
+    if (b > RED_MAX_BLOCKS) b = RED_MAX_BLOCKS;
+    return (int)b;
+}
+
+cudaError_t launch_dot(int dtype, i64 n, const void* x, const void* y, double* scratch, double* out2, cudaStream_t st) {
+    const int b = red_blocks(n);
+    HPCLA_DISPATCH_T(dtype, (dot_kernel<float><<<b, RED_THREADS, 0, st>>>(n, (const float*)x, (const float*)y, scratch, out2)),
+                     (dot_kernel<double><<<b, RED_THREADS, 0, st>>>(n, (const double*)x, (const double*)y, scratch, out2)),
+                     (dot_kernel<cplx><<<b, RED_THREADS, 0, st>>>(n, (const cplx*)x, (const cplx*)y, scratch, out2)));
+    return cudaGetLastError();
+}
+cudaError_t launch_axpby(int dtype, i64 n, const void* alpha, const void* x, const void* beta, void* y, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    i64 bl = (n + 1023) / 1024;
+    const int b = (int)(bl > 148 * 16 ? 148 * 16 : bl);
+    HPCLA_DISPATCH_T(dtype, (axpby_kernel<float><<<b, 256, 0, st>>>(n, Scal<float>{*(const float*)alpha}, (const float*)x, Scal<float>{*(const float*)beta}, (float*)y)),
+                     (axpby_kernel<double><<<b, 256, 0, st>>>(n, Scal<double>{*(const double*)alpha}, (const double*)x, Scal<double>{*(const double*)beta}, (double*)y)),
+                     (axpby_kernel<cplx><<<b, 256, 0, st>>>(n, Scal<cplx>{*(const cplx*)alpha}, (const cplx*)x, Scal<cplx>{*(const cplx*)beta}, (cplx*)y)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cg_init(int dtype, i64 n, const void* b, void* x, void* r, void* p, double* scratch, double* rr_out2, cudaStream_t st) {
+    const int g = red_blocks(n);
+    if (dtype == HPCLA_F32) cg_init_kernel<float><<<g, RED_THREADS, 0, st>>>(n, (const float*)b, (float*)x, (float*)r, (float*)p, scratch, rr_out2);
+    else if (dtype == HPCLA_F64) cg_init_kernel<double><<<g, RED_THREADS, 0, st>>>(n, (const double*)b, (double*)x, (double*)r, (double*)p, scratch, rr_out2);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+cudaError_t launch_cg_update_xr(int dtype, i64 n, const void* p, const void* q, void* x, void* r, const double* rr, const double* pq, double* scratch,
+                                double* rr_new_out2, cudaStream_t st) {
+    const int g = red_blocks(n);
+    if (dtype == HPCLA_F32)
+        cg_update_xr_kernel<float><<<g, RED_THREADS, 0, st>>>(n, (const float*)p, (const float*)q, (float*)x, (float*)r, rr, pq, scratch, rr_new_out2);
+    else if (dtype == HPCLA_F64)
+        cg_update_xr_kernel<double><<<g, RED_THREADS, 0, st>>>(n, (const double*)p, (const double*)q, (double*)x, (double*)r, rr, pq, scratch, rr_new_out2);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+cudaError_t launch_cg_update_p(int dtype, i64 n, const void* r, void* p, const double* rr_new, const double* rr, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    i64 bl = (n + 1023) / 1024;
+    const int g = (int)(bl > 148 * 16 ? 148 * 16 : bl);
+    if (dtype == HPCLA_F32) cg_update_p_kernel<float><<<g, 256, 0, st>>>(n, (const float*)r, (float*)p, rr_new, rr);
+    else if (dtype == HPCLA_F64) cg_update_p_kernel<double><<<g, 256, 0, st>>>(n, (const double*)r, (double*)p, rr_new, rr);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+}  // namespace hpcla

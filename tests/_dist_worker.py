@@ -1,0 +1,49 @@
+"""2-process gloo worker for tests/test_host_logic.py::test_gloo_world_size_2 (run under torch.distributed.run)."""
+import numpy as np
+import scipy.sparse as sp
+import torch.distributed as dist
+
+import hpcla_b200 as la
+from conftest import FIXTURES, fixture_matrix
+from oracle import oracle as orc
+from test_host_logic import _compare_matrix, _compare_plan
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, P = dist.get_rank(), dist.get_world_size()
+    comm = la.CommMPI()
+    rng = np.random.default_rng(5)
+    cases = [(fixture_matrix(f), f.get("row_partition"), np.complex128 if f["dtype"] == "c128" else np.float64) for f in FIXTURES]
+    R = sp.random(300, 280, density=0.03, random_state=rng, format="csr")
+    cases.append((R, None, np.float64))
+    cases.append((la.synth.stencil_matrix(la.synth.POISSON3D_7PT, 6, la.backend_cpu_serial()) and None, None, None))
+    for A_global, rp, T in cases:
+        if A_global is None:
+            continue
+        for Ti in (np.int32, np.int64):
+            b = la.backend_cpu_mpi(T, Ti, comm=comm)
+            A_global = sp.csr_matrix(A_global).astype(T)
+            A = la.HPCSparseMatrix.from_global(A_global, b, row_partition=rp)
+            olocs = orc.distribute(A_global, P, row_partition=rp, itype="i32" if Ti == np.int32 else "i64")
+            _compare_matrix(A, olocs[rank])
+            x = la.HPCVector.from_global(np.ones(A_global.shape[1], dtype=T), b)
+            plan = la.get_vector_plan(A, x)
+            _compare_plan(plan, orc.vector_plans(olocs, orc.uniform_partition(A_global.shape[1], P))[rank])
+            At = la.materialize_transpose(A)
+            _compare_matrix(At, orc.transpose(olocs)[rank])
+            assert np.array_equal(x.to_global(), np.ones(A_global.shape[1], dtype=T))
+    # locally generated rows (HPCSparseMatrix_local route) agree with distributing the global matrix
+    b = la.backend_cpu_mpi(np.float64, np.int32, comm=comm)
+    A = la.synth.stencil_matrix(la.synth.POISSON3D_7PT, 6, b)
+    rp_, c_, v_ = la.synth.stencil_local(la.synth.POISSON3D_7PT, 6, 0, 216, np.float64, np.int32)
+    G = sp.csr_matrix((v_, c_ - 1, rp_ - 1), shape=(216, 216))
+    _compare_matrix(A, orc.distribute(G, P, itype="i32")[rank])
+    assert la.comm_allreduce(comm, rank + 1) == P * (P + 1) // 2
+    dist.barrier()
+    print("DIST_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
