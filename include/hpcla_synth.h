@@ -15,15 +15,15 @@ extern "C" {
 #endif
 
 enum {
-    HPCLA_SYNTH_LAPLACE2D_5PT = 0, /* N x N grid, g = ix + N*iy, diag 4, neighbours -1, Dirichlet truncation          */
-    HPCLA_SYNTH_POISSON3D_7PT = 1, /* N^3 grid, g = ix + N*iy + N^2*iz, diag 6, neighbours -1                          */
+    HPCLA_SYNTH_LAPLACE2D_5PT = 0, /* nx x ny grid, g = ix + nx*iy, diag 4, neighbours -1, Dirichlet truncation (nz ignored) */
+    HPCLA_SYNTH_POISSON3D_7PT = 1, /* nx x ny x nz grid, g = ix + nx*iy + nx*ny*iz, diag 6, neighbours -1                      */
     HPCLA_SYNTH_STENCIL3D_27PT = 2 /* centre 26, others -1, plus 0.1*((2u1-1) + i(2u2-1)) keyed on (g*27+d): A^T != A  */
 };
 
-int64_t hpcla_synth_stencil_rows(int kind, int64_t N);
-int64_t hpcla_synth_stencil_nnz(int kind, int64_t N, int64_t row_begin, int64_t row_end);
-int hpcla_synth_stencil_fill(int kind, int64_t N, int dtype, int itype, int64_t row_begin, int64_t row_end, void* rowptr,
-                             void* global_cols, void* nzval);
+int64_t hpcla_synth_stencil_rows(int kind, int64_t nx, int64_t ny, int64_t nz);
+int64_t hpcla_synth_stencil_nnz(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t row_begin, int64_t row_end);
+int hpcla_synth_stencil_fill(int kind, int64_t nx, int64_t ny, int64_t nz, int dtype, int itype, int64_t row_begin,
+                             int64_t row_end, void* rowptr, void* global_cols, void* nzval);
 
 /* power-law rows: L_g = min(max_len, n, floor(7 * (1 - u(g))^(-1/1.5))) (Pareto, alpha 2.5, k_min 7); the k-th column
  * of row g is floor((k + u(g,k)) * n / L_g) (stratified: ascending and distinct); values 2u - 1. */

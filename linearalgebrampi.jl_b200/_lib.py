@@ -86,9 +86,9 @@ SIGNATURES = {
     "hpcla_axpby": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_cg": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     # include/hpcla_synth.h
-    "hpcla_synth_stencil_rows": (_i64, [_i, _i64]),
-    "hpcla_synth_stencil_nnz": (_i64, [_i, _i64, _i64, _i64]),
-    "hpcla_synth_stencil_fill": (_i, [_i, _i64, _i, _i, _i64, _i64, _vp, _vp, _vp]),
+    "hpcla_synth_stencil_rows": (_i64, [_i, _i64, _i64, _i64]),
+    "hpcla_synth_stencil_nnz": (_i64, [_i, _i64, _i64, _i64, _i64, _i64]),
+    "hpcla_synth_stencil_fill": (_i, [_i, _i64, _i64, _i64, _i, _i, _i64, _i64, _vp, _vp, _vp]),
     "hpcla_synth_powerlaw_nnz": (_i64, [_i64, _u64, _i64, _i64, _i64]),
     "hpcla_synth_powerlaw_fill": (_i, [_i64, _u64, _i64, _i, _i, _i64, _i64, _vp, _vp, _vp]),
     "hpcla_synth_vector": (_i, [_i, _u64, _i64, _i64, _vp]),

@@ -18,6 +18,7 @@ alone — there is no CPU fallback.
 """
 from __future__ import annotations
 
+import itertools
 import threading
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional
@@ -77,6 +78,9 @@ class SolverCuDSS(AbstractSolver):
 # ---------------------------------------------------------------------------------------------------------------
 # comms
 # ---------------------------------------------------------------------------------------------------------------
+_comm_uid = itertools.count(1)
+
+
 class AbstractComm:
     pass
 
@@ -97,6 +101,8 @@ class CommMPI(AbstractComm):
         if not dist.is_initialized():
             raise RuntimeError("CommMPI needs torch.distributed.init_process_group() first (the reference needs MPI.Init())")
         self.group = group
+        self.uid = next(_comm_uid)
+        self._ctxs = {}
         self._dist = dist
         self._host_group = None
         self.rank = dist.get_rank(group)
@@ -122,9 +128,11 @@ class ThreadWorld:
 
     def __init__(self, nranks: int):
         self.nranks = nranks
+        self.uid = next(_comm_uid)
         self.barrier = threading.Barrier(nranks)
         self.slots: List[Any] = [None] * nranks
-        self.ctxs: Dict[int, list] = {}
+        self.handles: Dict[Any, list] = {}  # device assignment -> raw context handles, while a group is being formed
+        self._ctxs: Dict[Any, Any] = {}  # (rank, device) -> DeviceContext
         self.lock = threading.Lock()
 
     def run(self, fn, *args):
@@ -326,8 +334,15 @@ class DeviceContext:
         _lib.check(_lib.lib().hpcla_ctx_sync(self.handle))
 
 
-_ctx_cache: Dict[Any, DeviceContext] = {}
+_serial_ctx_cache: Dict[int, DeviceContext] = {}  # CommSerial: one context per device
 _ctx_lock = threading.Lock()
+
+
+def comm_uid(comm: AbstractComm) -> int:
+    """Identity of a communicator that is never reused (unlike id()); part of the plan-cache key."""
+    if isinstance(comm, CommSerial):
+        return 0
+    return comm.world.uid if isinstance(comm, CommThreads) else comm.uid
 
 
 def _device_context(b: HPCBackend) -> DeviceContext:
@@ -342,10 +357,16 @@ def _device_context(b: HPCBackend) -> DeviceContext:
         raise _lib.HPCLAError("no CUDA device is visible: DeviceCUDA backends cannot run here (no CPU fallback)")
     ndev = torch.cuda.device_count()
     dev = b.device.index if b.device.index is not None else rank % ndev  # ext/HPCLinearAlgebraCUDAExt.jl:611-613
-    key = (id(comm) if not isinstance(comm, CommThreads) else ("threads", id(comm.world), rank), dev)
+    # contexts live on the communicator they belong to (never in a cache keyed by id(): ids are reused)
+    if isinstance(comm, CommSerial):
+        cache, key = _serial_ctx_cache, dev
+    elif isinstance(comm, CommThreads):
+        cache, key = comm.world._ctxs, (rank, dev)
+    else:
+        cache, key = comm._ctxs, dev
     with _ctx_lock:
-        if key in _ctx_cache:
-            return _ctx_cache[key]
+        if key in cache:
+            return cache[key]
     h = ctypes.c_void_p()
     _lib.check(L.hpcla_ctx_create(dev, rank, size, ctypes.byref(h)))
     if isinstance(comm, CommSerial) or size == 1:
@@ -362,16 +383,16 @@ def _device_context(b: HPCBackend) -> DeviceContext:
     else:
         w = comm.world
         with w.lock:
-            w.ctxs.setdefault(id(w), [None] * size)[rank] = h.value
+            w.handles.setdefault("forming", [None] * size)[rank] = h.value
         w.barrier.wait()
         if rank == 0:
-            arr = (ctypes.c_void_p * size)(*w.ctxs[id(w)])
+            arr = (ctypes.c_void_p * size)(*w.handles.pop("forming"))
             _lib.check(L.hpcla_ctx_form_group(arr, size))
         w.barrier.wait()
         world = "threads"
     ctx = DeviceContext(h.value, dev, rank, size, world)
     with _ctx_lock:
-        _ctx_cache[key] = ctx
+        cache[key] = ctx
     return ctx
 
 

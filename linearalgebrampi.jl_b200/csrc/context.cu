@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "device.h"
@@ -146,6 +147,7 @@ struct hpcla_spmv {
     void* cur_y = nullptr;
     cudaStream_t cur_stream = nullptr;
     int phase = 0;  // 0 idle, 1 multiply begun, 2 gather begun
+    std::atomic<long long> epoch{0};  // exchanges begun (a peer's finish checks that I have begun the matching one)
     i64 launches = 0;
 };
 
@@ -540,6 +542,7 @@ static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream) 
         }
     }
     CU_TRY(cudaEventRecord(op->ev_packed, hs));
+    op->epoch.fetch_add(1, std::memory_order_release);
     if (!group && ctx->comm) {
         NcclApi* api = nccl_api();
         size_t per = 1;
@@ -565,7 +568,7 @@ static int exchange_finish_group(hpcla_spmv* op) {
     cudaStream_t hs = ctx->halo_stream;
     for (const Seg& r : op->recvs) {
         hpcla_spmv* peer = group_peer(op, r.peer);
-        if (!peer || peer->phase == 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_finish: rank %d has not begun the matching multiply", r.peer);
+        if (!peer || peer->epoch.load(std::memory_order_acquire) < op->epoch.load(std::memory_order_acquire)) return fail(HPCLA_ERR_STATE, "hpcla_spmv_finish: rank %d has not begun the matching multiply", r.peer);
         const Seg* ps = nullptr;
         for (const Seg& s : peer->sends)
             if (s.peer == ctx->rank) ps = &s;

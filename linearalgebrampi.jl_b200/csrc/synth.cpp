@@ -36,14 +36,17 @@ void pfor_rows(i64 b, i64 e, F f) {
     for (auto& x : th) x.join();
 }
 
-inline int stencil_row_len(int kind, i64 N, i64 g) {
+struct Grid {
+    i64 nx, ny, nz;
+};
+inline int stencil_row_len(int kind, Grid G, i64 g) {
     if (kind == HPCLA_SYNTH_LAPLACE2D_5PT) {
-        i64 ix = g % N, iy = g / N;
-        return 1 + (ix > 0) + (ix < N - 1) + (iy > 0) + (iy < N - 1);
+        i64 ix = g % G.nx, iy = g / G.nx;
+        return 1 + (ix > 0) + (ix < G.nx - 1) + (iy > 0) + (iy < G.ny - 1);
     }
-    i64 ix = g % N, iy = (g / N) % N, iz = g / (N * N);
-    if (kind == HPCLA_SYNTH_POISSON3D_7PT) return 1 + (ix > 0) + (ix < N - 1) + (iy > 0) + (iy < N - 1) + (iz > 0) + (iz < N - 1);
-    int cx = 1 + (ix > 0) + (ix < N - 1), cy = 1 + (iy > 0) + (iy < N - 1), cz = 1 + (iz > 0) + (iz < N - 1);
+    i64 ix = g % G.nx, iy = (g / G.nx) % G.ny, iz = g / (G.nx * G.ny);
+    if (kind == HPCLA_SYNTH_POISSON3D_7PT) return 1 + (ix > 0) + (ix < G.nx - 1) + (iy > 0) + (iy < G.ny - 1) + (iz > 0) + (iz < G.nz - 1);
+    int cx = 1 + (ix > 0) + (ix < G.nx - 1), cy = 1 + (iy > 0) + (iy < G.ny - 1), cz = 1 + (iz > 0) + (iz < G.nz - 1);
     return cx * cy * cz;
 }
 
@@ -54,37 +57,38 @@ struct c128 { double re, im; };
 template <> struct Val<c128> { static c128 make(double re, double im) { return c128{re, im}; } };
 
 template <class T, class Ti>
-void stencil_fill_rows(int kind, i64 N, i64 row_begin, i64 lo, i64 hi, const Ti* rowptr, Ti* cols, T* vals) {
+void stencil_fill_rows(int kind, Grid G, i64 row_begin, i64 lo, i64 hi, const Ti* rowptr, Ti* cols, T* vals) {
+    const i64 NX = G.nx, NY = G.ny, NZ = G.nz, NXY = G.nx * G.ny;
     for (i64 g = lo; g < hi; ++g) {
         i64 k = (i64)rowptr[g - row_begin] - 1;
         if (kind == HPCLA_SYNTH_LAPLACE2D_5PT) {
-            i64 ix = g % N, iy = g / N;
-            if (iy > 0) cols[k] = (Ti)(g - N + 1), vals[k++] = Val<T>::make(-1, 0);
+            i64 ix = g % NX, iy = g / NX;
+            if (iy > 0) cols[k] = (Ti)(g - NX + 1), vals[k++] = Val<T>::make(-1, 0);
             if (ix > 0) cols[k] = (Ti)(g - 1 + 1), vals[k++] = Val<T>::make(-1, 0);
             cols[k] = (Ti)(g + 1), vals[k++] = Val<T>::make(4, 0);
-            if (ix < N - 1) cols[k] = (Ti)(g + 1 + 1), vals[k++] = Val<T>::make(-1, 0);
-            if (iy < N - 1) cols[k] = (Ti)(g + N + 1), vals[k++] = Val<T>::make(-1, 0);
+            if (ix < NX - 1) cols[k] = (Ti)(g + 1 + 1), vals[k++] = Val<T>::make(-1, 0);
+            if (iy < NY - 1) cols[k] = (Ti)(g + NX + 1), vals[k++] = Val<T>::make(-1, 0);
         } else if (kind == HPCLA_SYNTH_POISSON3D_7PT) {
-            i64 ix = g % N, iy = (g / N) % N, iz = g / (N * N);
-            if (iz > 0) cols[k] = (Ti)(g - N * N + 1), vals[k++] = Val<T>::make(-1, 0);
-            if (iy > 0) cols[k] = (Ti)(g - N + 1), vals[k++] = Val<T>::make(-1, 0);
+            i64 ix = g % NX, iy = (g / NX) % NY, iz = g / NXY;
+            if (iz > 0) cols[k] = (Ti)(g - NXY + 1), vals[k++] = Val<T>::make(-1, 0);
+            if (iy > 0) cols[k] = (Ti)(g - NX + 1), vals[k++] = Val<T>::make(-1, 0);
             if (ix > 0) cols[k] = (Ti)(g), vals[k++] = Val<T>::make(-1, 0);
             cols[k] = (Ti)(g + 1), vals[k++] = Val<T>::make(6, 0);
-            if (ix < N - 1) cols[k] = (Ti)(g + 2), vals[k++] = Val<T>::make(-1, 0);
-            if (iy < N - 1) cols[k] = (Ti)(g + N + 1), vals[k++] = Val<T>::make(-1, 0);
-            if (iz < N - 1) cols[k] = (Ti)(g + N * N + 1), vals[k++] = Val<T>::make(-1, 0);
+            if (ix < NX - 1) cols[k] = (Ti)(g + 2), vals[k++] = Val<T>::make(-1, 0);
+            if (iy < NY - 1) cols[k] = (Ti)(g + NX + 1), vals[k++] = Val<T>::make(-1, 0);
+            if (iz < NZ - 1) cols[k] = (Ti)(g + NXY + 1), vals[k++] = Val<T>::make(-1, 0);
         } else {
-            i64 ix = g % N, iy = (g / N) % N, iz = g / (N * N);
+            i64 ix = g % NX, iy = (g / NX) % NY, iz = g / NXY;
             int d = 0;
             for (int dz = -1; dz <= 1; ++dz)
                 for (int dy = -1; dy <= 1; ++dy)
                     for (int dx = -1; dx <= 1; ++dx, ++d) {
                         i64 jx = ix + dx, jy = iy + dy, jz = iz + dz;
-                        if (jx < 0 || jx >= N || jy < 0 || jy >= N || jz < 0 || jz >= N) continue;
+                        if (jx < 0 || jx >= NX || jy < 0 || jy >= NY || jz < 0 || jz >= NZ) continue;
                         uint64_t key = (uint64_t)(g * 27 + d);
                         double re = (d == 13 ? 26.0 : -1.0) + 0.1 * (2.0 * unit(STENCIL_SEED, 2 * key) - 1.0);
                         double im = 0.1 * (2.0 * unit(STENCIL_SEED, 2 * key + 1) - 1.0);
-                        cols[k] = (Ti)(jx + N * jy + N * N * jz + 1);
+                        cols[k] = (Ti)(jx + NX * jy + NXY * jz + 1);
                         vals[k++] = Val<T>::make(re, im);
                     }
         }
@@ -92,7 +96,7 @@ void stencil_fill_rows(int kind, i64 N, i64 row_begin, i64 lo, i64 hi, const Ti*
 }
 
 template <class T, class Ti>
-int stencil_fill_typed(int kind, i64 N, i64 rb, i64 re, Ti* rowptr, Ti* cols, T* vals) {
+int stencil_fill_typed(int kind, Grid N, i64 rb, i64 re, Ti* rowptr, Ti* cols, T* vals) {
     i64 acc = 1;
     for (i64 g = rb; g < re; ++g) {
         rowptr[g - rb] = (Ti)acc;
@@ -142,9 +146,10 @@ int powerlaw_fill_typed(i64 n, uint64_t seed, i64 max_len, i64 rb, i64 re, Ti* r
 }
 }  // namespace
 
-extern "C" int64_t hpcla_synth_stencil_rows(int kind, int64_t N) { return kind == HPCLA_SYNTH_LAPLACE2D_5PT ? N * N : N * N * N; }
+extern "C" int64_t hpcla_synth_stencil_rows(int kind, int64_t nx, int64_t ny, int64_t nz) { return kind == HPCLA_SYNTH_LAPLACE2D_5PT ? nx * ny : nx * ny * nz; }
 
-extern "C" int64_t hpcla_synth_stencil_nnz(int kind, int64_t N, int64_t rb, int64_t re) {
+extern "C" int64_t hpcla_synth_stencil_nnz(int kind, int64_t nx, int64_t ny, int64_t nz, int64_t rb, int64_t re) {
+    Grid N{nx, ny, nz};
     i64 acc = 0;
     for (i64 g = rb; g < re; ++g) acc += stencil_row_len(kind, N, g);
     return acc;
@@ -161,8 +166,11 @@ extern "C" int64_t hpcla_synth_stencil_nnz(int kind, int64_t N, int64_t rb, int6
         return fail(HPCLA_ERR_ARG, "synth: unknown dtype/itype");                                                 \
     } while (0)
 
-extern "C" int hpcla_synth_stencil_fill(int kind, int64_t N, int dtype, int itype, int64_t rb, int64_t re, void* rowptr, void* global_cols, void* nzval) {
-    if (kind < 0 || kind > 2 || N < 1 || rb < 0 || re < rb || re > hpcla_synth_stencil_rows(kind, N)) return fail(HPCLA_ERR_ARG, "hpcla_synth_stencil_fill: bad arguments");
+extern "C" int hpcla_synth_stencil_fill(int kind, int64_t nx, int64_t ny, int64_t nz, int dtype, int itype, int64_t rb, int64_t re, void* rowptr, void* global_cols,
+                                        void* nzval) {
+    if (kind < 0 || kind > 2 || nx < 1 || ny < 1 || nz < 1 || rb < 0 || re < rb || re > hpcla_synth_stencil_rows(kind, nx, ny, nz))
+        return fail(HPCLA_ERR_ARG, "hpcla_synth_stencil_fill: bad arguments");
+    Grid N{nx, ny, nz};
     SYNTH_DISPATCH(stencil_fill_typed, kind, N, rb, re);
 }
 

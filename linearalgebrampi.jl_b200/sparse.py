@@ -18,6 +18,7 @@ backends.py (the reference does it with MPI at the same places).
 from __future__ import annotations
 
 import ctypes
+import itertools
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -32,6 +33,7 @@ from .backends import (
     comm_exchange,
     comm_rank,
     comm_size,
+    comm_uid,
 )
 from .vectors import HPCVector, _current_stream, _digest, _to_device, _torch_dtype, compute_partition_hash, uniform_partition
 
@@ -213,13 +215,12 @@ def _ensure_hash(A: HPCSparseMatrix) -> bytes:
 class VectorPlan:
     """VectorPlan{T,Ti,AV} (src/vectors.jl:229-251): the index fields, exported from the library's plan object."""
 
-    _next_uid = 0
+    _uids = itertools.count(1)
 
     def __init__(self, handle: int, Ti, n_x_local: int):
         L = _lib.lib()
         self.handle = handle
-        VectorPlan._next_uid += 1
-        self.uid = VectorPlan._next_uid
+        self.uid = next(VectorPlan._uids)
         self.n_x_local = n_x_local
         Ti = np.dtype(Ti)
 
@@ -300,7 +301,7 @@ def get_vector_plan(A: HPCSparseMatrix, x: HPCVector) -> VectorPlan:
 
 def _comm_key(b: HPCBackend):
     # one python process may host several ranks (CommThreads): their plans differ, so the rank is part of the key
-    return (id(getattr(b.comm, "world", None)), comm_rank(b.comm))
+    return (comm_uid(b.comm), comm_rank(b.comm))
 
 
 def clear_plan_cache() -> None:

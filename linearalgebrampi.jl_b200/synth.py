@@ -16,21 +16,29 @@ LAPLACE2D_5PT, POISSON3D_7PT, STENCIL3D_27PT = 0, 1, 2
 X_SEED = 0x5EED
 
 
-def stencil_rows(kind: int, N: int) -> int:
-    return int(_lib.lib().hpcla_synth_stencil_rows(kind, N))
+def _grid(N):
+    """N: an int (square / cubic grid) or a tuple (nx, ny[, nz])."""
+    if isinstance(N, (int, np.integer)):
+        return int(N), int(N), int(N)
+    g = tuple(int(v) for v in N)
+    return (g[0], g[1], 1) if len(g) == 2 else g
 
 
-def stencil_local(kind: int, N: int, row_begin: int, row_end: int, T, Ti):
+def stencil_rows(kind: int, N) -> int:
+    return int(_lib.lib().hpcla_synth_stencil_rows(kind, *_grid(N)))
+
+
+def stencil_local(kind: int, N, row_begin: int, row_end: int, T, Ti):
     """Rows [row_begin, row_end) (0-based) -> (rowptr 1-based, GLOBAL columns 1-based, values)."""
     L = _lib.lib()
     T, Ti = np.dtype(T), np.dtype(Ti)
-    nnz = int(L.hpcla_synth_stencil_nnz(kind, N, row_begin, row_end))
+    nnz = int(L.hpcla_synth_stencil_nnz(kind, *_grid(N), row_begin, row_end))
     if Ti == np.int32 and nnz >= 2**31 - 1:
         raise _lib.HPCLAError("local nnz does not fit Int32 row pointers")
     rowptr = np.empty(row_end - row_begin + 1, dtype=Ti)
     cols = np.empty(nnz, dtype=Ti)
     vals = np.empty(nnz, dtype=T)
-    _lib.check(L.hpcla_synth_stencil_fill(kind, N, _lib.dtype_code(T), _lib.itype_code(Ti), row_begin, row_end, _lib.ptr(rowptr), _lib.ptr(cols), _lib.ptr(vals)))
+    _lib.check(L.hpcla_synth_stencil_fill(kind, *_grid(N), _lib.dtype_code(T), _lib.itype_code(Ti), row_begin, row_end, _lib.ptr(rowptr), _lib.ptr(cols), _lib.ptr(vals)))
     return rowptr, cols, vals
 
 
@@ -60,7 +68,7 @@ def _my_rows(n: int, backend: HPCBackend):
     return part, int(part[r]) - 1, int(part[r + 1]) - 1
 
 
-def stencil_matrix(kind: int, N: int, backend: HPCBackend) -> HPCSparseMatrix:
+def stencil_matrix(kind: int, N, backend: HPCBackend) -> HPCSparseMatrix:
     n = stencil_rows(kind, N)
     part, b, e = _my_rows(n, backend)
     rowptr, cols, vals = stencil_local(kind, N, b, e, backend.T, backend.Ti)

@@ -1,0 +1,330 @@
+"""GPU parity tests: the CUDA path, called through the C ABI of libhpcla_b200.so (via the python mirror of the
+reference API), against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): ||y - y_ref||_2 / ||y_ref||_2 <= 1e-12 (Float64, ComplexF64), <= 1e-5 (Float32);
+plan arrays, ghost maps and the gathered vector bit-exact.  Multi-rank cases on a single GPU run as a single-process
+world of rank-threads (device-to-device copies stand in for ncclSend/ncclRecv; kernels, pack, interior/boundary split and
+ghost addressing are the same code)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import hpcla_b200 as la
+from conftest import FIXTURES, fixture_matrix
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12, np.dtype(np.complex128): 1e-12}
+ALL_TYPES = [(np.float32, np.int32), (np.float32, np.int64), (np.float64, np.int32), (np.float64, np.int64),
+             (np.complex128, np.int32), (np.complex128, np.int64)]
+
+
+def relerr(y, ref):
+    d = np.linalg.norm(np.asarray(y, dtype=np.complex128) - np.asarray(ref, dtype=np.complex128))
+    return d / max(np.linalg.norm(np.asarray(ref, dtype=np.complex128)), 1e-300)
+
+
+def backends(P, T, Ti):
+    return [la.backend_cuda_serial(T, Ti)] if P == 1 else la.backends_threads(P, T, Ti, cuda=True)
+
+
+def spmd(bs, fn, *args):
+    if len(bs) == 1:
+        return [fn(0, bs, *args)]
+    return bs[0].comm.world.run(fn, bs, *args)
+
+
+def _matvec_body(rank, bs, A_global, x_global, row_partition, x_partition, want_gathered, use_mul):
+    b = bs[rank]
+    torch.cuda.set_device(b.torch_device())
+    A = la.HPCSparseMatrix.from_global(A_global, b, row_partition=row_partition)
+    x = la.HPCVector.from_global(x_global, b, partition=x_partition)
+    out = {}
+    if want_gathered:
+        g = la.execute_plan(la.get_vector_plan(A, x), A, x)
+        torch.cuda.synchronize()
+        out["gathered"] = g.cpu().numpy().copy()
+    if use_mul:
+        y = la.HPCVector.zeros(b, A_global.shape[0], partition=A.row_partition)
+        y.v.fill_(float("nan"))
+        assert la.mul(y, A, x) is y
+    else:
+        y = A * x
+    assert y.partition.tolist() == A.row_partition.tolist() and y.backend is b and y.v.is_cuda
+    out["y"] = y.to_global()
+    out["info"] = la.spmv_info(A, x)
+    At = la.materialize_transpose(A)
+    xT = la.HPCVector.from_global(np.resize(x_global, A_global.shape[0]), b, partition=A.row_partition)
+    yT = la.transpose(A) @ xT
+    assert yT.partition.tolist() == A.col_partition.tolist()
+    out["yT"] = yT.to_global()
+    out["xT"] = xT.to_global()
+    del At
+    return out
+
+
+def run_case(A_global, x_global, P, T, Ti, row_partition=None, x_partition=None, want_gathered=True, use_mul=False):
+    A_global = sp.csr_matrix(A_global).astype(T)
+    x_global = np.asarray(x_global).astype(T)
+    la.clear_plan_cache()
+    res = spmd(backends(P, T, Ti), _matvec_body, A_global, x_global, row_partition, x_partition, want_gathered, use_mul)
+    itype = "i32" if Ti == np.int32 else "i64"
+    olocs = orc.distribute(A_global, P, row_partition=row_partition, itype=itype)
+    xp = orc.uniform_partition(A_global.shape[1], P) if x_partition is None else np.asarray(x_partition, dtype=np.int64)
+    y_ref = orc.matvec(olocs, x_global, xp)
+    for r in range(P):
+        assert relerr(res[r]["y"], y_ref) <= TOL[np.dtype(T)], (r, relerr(res[r]["y"], y_ref))
+    if want_gathered:
+        W = orc.PlanWorld(olocs, xp)
+        g_ref = W.execute(orc.split_vector(x_global, xp))
+        W.close()
+        for r in range(P):
+            assert np.array_equal(res[r]["gathered"], g_ref[r]), f"gathered differs on rank {r}"
+    yT_ref = orc.matvec(orc.transpose(olocs), res[0]["xT"])
+    assert relerr(res[0]["yT"], yT_ref) <= TOL[np.dtype(T)]
+    return res, y_ref
+
+
+@pytest.mark.parametrize("fx", FIXTURES, ids=[f["name"] for f in FIXTURES])
+def test_reference_fixtures_on_device(fx):
+    """The reference's own test cases (test/test_vector_multiplication.jl etc.), A*x and mul!, 1/2/3 ranks."""
+    T = np.complex128 if fx["dtype"] == "c128" else np.float64
+    A = fixture_matrix(fx)
+    for P, Ti, use_mul in [(1, np.int64, False), (2, np.int64, True), (2, np.int32, False), (3, np.int32, True)]:
+        rp = fx.get("row_partition") if P == 2 else None
+        res, _ = run_case(A, fx["x"], P, T, Ti, row_partition=rp, use_mul=use_mul)
+        assert np.max(np.abs(res[0]["y"] - fx["y"])) < fx["tol"]  # the test's own tolerance (test_utils.jl:154-157)
+
+
+@pytest.mark.parametrize("fx", [f for f in FIXTURES if "yT" in f], ids=[f["name"] for f in FIXTURES if "yT" in f])
+def test_reference_fixtures_transpose_paths(fx):
+    """transpose(A)*x, transpose(x)*A and x'*A (test_vector_multiplication.jl:141-159, test_new_operations.jl:73-76)."""
+    T = np.complex128 if fx["dtype"] == "c128" else np.float64
+
+    def body(rank, bs):
+        b = bs[rank]
+        torch.cuda.set_device(b.torch_device())
+        A = la.HPCSparseMatrix.from_global(fixture_matrix(fx), b)
+        x = la.HPCVector.from_global(fx.get("xT", fx["x"]), b, partition=A.row_partition)
+        out = {"yT": (la.transpose(A) * x).to_global(), "vtA": la.vec_transpose_mul(x, A).to_global()}
+        if "y_adj" in fx:
+            out["adj"] = la.vec_adjoint_mul(x, A).to_global()
+        if "dot_xy" in fx:
+            y0 = la.HPCVector.from_global(fx["dot_with"], b)
+            out["dot_xy"], out["dot_xx"], out["nrm"] = la.dot(x, y0), la.dot(x, x), la.norm(x)
+        return out
+
+    for P in (1, 2):
+        la.clear_plan_cache()
+        for r in spmd(backends(P, T, np.int64), body):
+            assert np.max(np.abs(r["yT"] - fx["yT"])) < fx["tol"] and np.max(np.abs(r["vtA"] - fx["yT"])) < fx["tol"]
+            if "adj" in r:
+                assert np.max(np.abs(r["adj"] - fx["y_adj"])) < fx["tol"]
+            if "dot_xy" in r:
+                assert abs(r["dot_xy"] - fx["dot_xy"]) < fx["tol"] and abs(r["dot_xx"] - fx["dot_xx"]) < fx["tol"]
+                assert abs(r["nrm"] - np.linalg.norm(fx["x"])) < fx["tol"]
+
+
+def _ragged(rng, m, n, dens, T, long_rows=()):
+    A = sp.random(m, n, density=dens, random_state=rng, format="lil")
+    for r, L in long_rows:
+        cols = rng.choice(n, size=min(L, n), replace=False)
+        A[r, cols] = 1.0
+    A = sp.csr_matrix(A)
+    A.data = rng.uniform(-1, 1, A.nnz)
+    if np.dtype(T).kind == "c":
+        A = A.astype(np.complex128)
+        A.data = A.data + 1j * rng.uniform(-1, 1, A.nnz)
+    A = sp.csr_matrix(sp.diags(np.r_[0.0, np.ones(m - 2), 0.0]) @ A)  # first/last rows empty
+    A.eliminate_zeros()
+    A.sort_indices()
+    return A.astype(T)
+
+
+def _vec(rng, n, T):
+    x = rng.uniform(-1, 1, n)
+    if np.dtype(T).kind == "c":
+        x = x + 1j * rng.uniform(-1, 1, n)
+    return x.astype(T)
+
+
+@pytest.mark.parametrize("T,Ti", ALL_TYPES, ids=[f"{np.dtype(t).name}-{np.dtype(i).name}" for t, i in ALL_TYPES])
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_random_ragged_all_types(T, Ti, P):
+    rng = np.random.default_rng(42 + P)
+    for (m, n, dens) in [(257, 300, 0.05), (3000, 3000, 0.004), (40, 5000, 0.2)]:
+        run_case(_ragged(rng, m, n, dens, T), _vec(rng, n, T), P, T, Ti)
+
+
+@pytest.mark.parametrize("P", [1, 3])
+def test_every_row_length_regime(P):
+    """Tiles reduced by 1..32 lanes per row, tiles that do not fit shared memory (warp-per-row), split long rows."""
+    rng = np.random.default_rng(7)
+    for T, Ti in [(np.float64, np.int32), (np.float32, np.int64), (np.complex128, np.int32)]:
+        for mean_len in (3, 20, 40, 80, 150, 400):
+            m, n = 600, 4000
+            A = _ragged(rng, m, n, mean_len / n, T)
+            run_case(A, _vec(rng, n, T), P, T, Ti, want_gathered=False)
+        # rows of 3k (does not fit a tile -> warp per row) and 40k / 70k (split across CTAs), among short rows
+        m, n = 500, 80000
+        A = _ragged(rng, m, n, 5 / n, T, long_rows=[(10, 3000), (200, 40000), (201, 70000), (430, 17000)])
+        res, _ = run_case(A, _vec(rng, n, T), P, T, Ti, want_gathered=False)
+        if P == 1:
+            assert res[0]["info"]["long_rows"] == 3
+
+
+def test_partitions_with_empty_ranks_and_foreign_x_partition():
+    rng = np.random.default_rng(3)
+    A = _ragged(rng, 90, 70, 0.1, np.float64)
+    x = _vec(rng, 70, np.float64)
+    run_case(A, x, 3, np.float64, np.int32, row_partition=np.array([1, 46, 46, 91]), x_partition=np.array([1, 11, 61, 71]))
+    run_case(A, x, 4, np.float64, np.int64, row_partition=np.array([1, 1, 31, 91, 91]), x_partition=np.array([1, 71, 71, 71, 71]))
+    # a matrix whose own column block has holes: x.v cannot be read in place, the local-copy path runs
+    B = sp.lil_matrix((64, 64))
+    for i in range(64):
+        B[i, (i * 2) % 64] = 1.0 + i
+        B[i, (i * 2 + 6) % 64] = -2.0
+    res, _ = run_case(sp.csr_matrix(B), _vec(rng, 64, np.float64), 2, np.float64, np.int32)
+    assert res[0]["info"]["x_in_place"] == 0
+
+
+@pytest.mark.parametrize("kind,N,T", [(0, 97, np.float64), (1, 40, np.float64), (1, 33, np.float32), (2, 20, np.complex128)])
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_synthetic_stencils(kind, N, T, P):
+    """The BASELINE generators at test size; Float64 stencil rows (<= 12 entries, one lane per row, products rounded
+    separately) reproduce the reference's summation order exactly => bit-identical y."""
+    S = la.synth
+    n = S.stencil_rows(kind, N)
+    rp, c, v = S.stencil_local(kind, N, 0, n, T, np.int32)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    x = S.vector_local(T, S.X_SEED, 0, n)
+
+    def body(rank, bs):
+        b = bs[rank]
+        torch.cuda.set_device(b.torch_device())
+        A = S.stencil_matrix(kind, N, b)
+        xv = S.vector(n, b)
+        y = A * xv
+        yT = la.transpose(A) * xv
+        return y.to_global(), yT.to_global(), la.spmv_info(A, xv)
+
+    la.clear_plan_cache()
+    res = spmd(backends(P, T, np.int32), body)
+    olocs = orc.distribute(G, P, itype="i32")
+    y_ref = orc.matvec(olocs, x)
+    yT_ref = orc.matvec(orc.transpose(olocs), x)
+    for y, yT, info in res:
+        assert relerr(y, y_ref) <= TOL[np.dtype(T)] and relerr(yT, yT_ref) <= TOL[np.dtype(T)]
+        if kind in (0, 1):
+            assert np.array_equal(y, y_ref), "short-row path must be bit-identical to the reference's summation order"
+        assert info["x_in_place"] == 1 and info["sends_contiguous"] == 1
+        if P > 1:
+            assert info["boundary_tiles"] > 0 and info["interior_tiles"] > 0
+
+
+def test_powerlaw_load_balance_case_small():
+    S = la.synth
+    n = 60000
+    rp, c, v = S.powerlaw_local(n, 0xC4, 30000, 0, n, np.float32, np.int32)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    x = S.vector_local(np.float32, S.X_SEED, 0, n)
+    for P in (1, 2):
+        def body(rank, bs):
+            torch.cuda.set_device(bs[rank].torch_device())
+            A = S.powerlaw_matrix(n, bs[rank], max_len=30000)
+            return (A * S.vector(n, bs[rank])).to_global()
+
+        la.clear_plan_cache()
+        res = spmd(backends(P, np.float32, np.int32), body)
+        y_ref = orc.matvec(orc.distribute(G, P, itype="i32"), x)
+        assert relerr(res[0], y_ref) <= 1e-5
+
+
+def test_memoised_plan_and_in_place_value_updates():
+    b = la.backend_cuda_serial(np.float64, np.int32)
+    A = la.synth.stencil_matrix(1, 16, b)
+    x = la.synth.vector(16**3, b)
+    la.clear_plan_cache()
+    n0 = la.sparse.plan_build_count
+    y1 = (A * x).to_global()
+    y2 = (A * x).to_global()
+    assert la.sparse.plan_build_count == n0 + 1 and np.array_equal(y1, y2)
+    A.nzval.mul_(2.0)  # in-place value write keeps the structure hash and the plan (src/indexing.jl:932-982)
+    A.values_changed()
+    assert np.array_equal((A * x).to_global(), 2.0 * y1) and la.sparse.plan_build_count == n0 + 1
+    info = la.spmv_info(A, x)
+    assert info["launches"] == 3 and info["boundary_tiles"] == 0  # one kernel per multiply on a single rank
+
+
+def test_vector_ops_and_cg():
+    for T in (np.float64, np.float32):
+        b = la.backend_cuda_serial(T, np.int32)
+        N = 12
+        n = N**3
+        A = la.synth.stencil_matrix(1, N, b)
+        rng = np.random.default_rng(0)
+        xh, yh = rng.uniform(-1, 1, n).astype(T), rng.uniform(-1, 1, n).astype(T)
+        x, y = la.HPCVector.from_global(xh, b), la.HPCVector.from_global(yh, b)
+        tol = 1e-5 if T == np.float32 else 1e-12
+        assert abs(la.dot(x, y) - np.dot(xh.astype(np.float64), yh.astype(np.float64))) <= tol * n
+        assert abs(la.norm(x) - np.linalg.norm(xh.astype(np.float64))) <= tol * n
+        la.axpby(0.5, x, -2.0, y)
+        assert relerr(y.to_global(), 0.5 * xh - 2.0 * yh) <= tol
+        # CG against the oracle's textbook CG on the same matrix
+        rp, c, v = la.synth.stencil_local(1, N, 0, n, T, np.int32)
+        G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+        bvec = (G @ np.ones(n)).astype(T)
+        sol, hist = la.cg(A, la.HPCVector.from_global(bvec, b), 25)
+        xo, ho = orc.cg(orc.distribute(G, 1, itype="i32"), bvec.astype(np.float64), 25)
+        assert relerr(sol.to_global(), xo) <= (1e-3 if T == np.float32 else 1e-9)
+        assert np.allclose(hist, np.array(ho, dtype=np.float64), rtol=1e-2 if T == np.float32 else 1e-8)
+    bc = la.backend_cuda_serial(np.complex128, np.int64)
+    xh = rng.uniform(-1, 1, 1000) + 1j * rng.uniform(-1, 1, 1000)
+    yh = rng.uniform(-1, 1, 1000) + 1j * rng.uniform(-1, 1, 1000)
+    x, y = la.HPCVector.from_global(xh, bc), la.HPCVector.from_global(yh, bc)
+    assert abs(la.dot(x, y) - np.vdot(xh, yh)) <= 1e-10  # Julia's dot conjugates its first argument
+
+
+def test_distributed_dot_norm_threads():
+    def body(rank, bs):
+        torch.cuda.set_device(bs[rank].torch_device())
+        x = la.synth.vector(10007, bs[rank])
+        y = la.synth.vector(10007, bs[rank], seed=99)
+        return la.dot(x, y), la.norm(x)
+
+    xh = la.synth.vector_local(np.float64, la.synth.X_SEED, 0, 10007)
+    yh = la.synth.vector_local(np.float64, 99, 0, 10007)
+    for d, nr in spmd(backends(3, np.float64, np.int64), body):
+        assert abs(d - np.dot(xh, yh)) <= 1e-10 and abs(nr - np.linalg.norm(xh)) <= 1e-10
+
+
+def test_full_size_poisson_256_properties():
+    """BASELINE config 2 (3-D 7-point Poisson 256^3, Float64/Int32) at full size: size-independent properties plus the
+    oracle's row-serial result on the whole vector (bit-identical: 7 entries per row, one lane per row)."""
+    S = la.synth
+    N = 256
+    n = N**3
+    b = la.backend_cuda_serial(np.float64, np.int32)
+    A = S.stencil_matrix(1, N, b)
+    assert A.nnz_local == 117047296 and A.shape == (n, n)
+    ones = la.HPCVector.from_global(np.ones(n), b)
+    y1 = (A * ones).local_values()
+    g = np.arange(n)
+    ix, iy, iz = g % N, (g // N) % N, g // (N * N)
+    expect = ((ix == 0).astype(float) + (ix == N - 1) + (iy == 0) + (iy == N - 1) + (iz == 0) + (iz == N - 1))
+    assert np.array_equal(y1, expect)  # row sums: 6 - (#neighbours)
+    x = S.vector(n, b)
+    y = A * x
+    # linearity: A(2x + 1) == 2Ax + A1
+    z = x.copy()
+    la.axpby(1.0, ones, 2.0, z)
+    lin = (A * z).local_values() - (2.0 * y.local_values() + y1)
+    assert np.linalg.norm(lin) <= 1e-12 * np.linalg.norm(y.local_values())
+    rp, c, v = S.stencil_local(1, N, 0, n, np.float64, np.int32)
+    L = orc.LocalMatrix(0, A.row_partition, A.col_partition, A.col_indices, rp, c, v, n, n)  # all columns present: colval == global col
+    y_ref = orc.spmv_local(L, x.local_values())
+    assert np.array_equal(y.local_values(), y_ref)
+    # symmetric operator: transpose(A)*x == A*x
+    assert relerr((la.transpose(A) * x).local_values(), y_ref) <= 1e-12

@@ -236,9 +236,16 @@ def test_synthetic_generators():
     assert abs(got - ref).max() == 0
     # counts of SURVEY App. A: nnz = 5n-4N, 7n-6N^2, (3N-2)^3
     L = la._lib.lib()
-    assert L.hpcla_synth_stencil_nnz(0, 1000, 0, 10**6) == 4996000
-    assert L.hpcla_synth_stencil_nnz(1, 64, 0, 64**3) == 7 * 64**3 - 6 * 64**2
-    assert L.hpcla_synth_stencil_nnz(2, 12, 0, 12**3) == (3 * 12 - 2) ** 3
+    assert L.hpcla_synth_stencil_nnz(0, 1000, 1000, 1, 0, 10**6) == 4996000
+    assert L.hpcla_synth_stencil_nnz(1, 64, 64, 64, 0, 64**3) == 7 * 64**3 - 6 * 64**2
+    assert L.hpcla_synth_stencil_nnz(2, 12, 12, 12, 0, 12**3) == (3 * 12 - 2) ** 3
+    # non-cubic grid (weak-scaling slabs): same operator as the kron construction
+    nx, ny, nz = 4, 3, 5
+    Lx, Ly, Lz = [sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(k, k)) for k in (nx, ny, nz)]
+    ref = sp.csr_matrix(sp.kron(sp.kron(sp.identity(nz), sp.identity(ny)), Lx) + sp.kron(sp.kron(sp.identity(nz), Ly), sp.identity(nx))
+                        + sp.kron(sp.kron(Lz, sp.identity(ny)), sp.identity(nx)))
+    rp3, c3, v3 = S.stencil_local(S.POISSON3D_7PT, (nx, ny, nz), 0, nx * ny * nz, np.float64, np.int32)
+    assert abs(sp.csr_matrix((v3, c3 - 1, rp3 - 1), shape=(60, 60)) - ref).max() == 0
     # row slices agree with the whole, for the 27-point complex stencil
     N = 6
     rp, c, v = S.stencil_local(S.STENCIL3D_27PT, N, 0, N**3, np.complex128, np.int32)
