@@ -1,0 +1,174 @@
+# HPCLinearAlgebraB200Ext.jl — the reference-side binding of libhpcla_b200.so.
+#
+# STATUS: written against the reference's sources (file:line cited below) but NEVER EXECUTED: this image has no
+# julia, no MPI and no CUDA.jl.  It is the stub a maintainer would add next to ext/HPCLinearAlgebraCUDAExt.jl;
+# INTEGRATION.md walks through it.  The python mirror under linearalgebrampi.jl_b200/ drives the very same C ABI
+# and is what the tests and benchmarks run.
+#
+# What it does: for DeviceCUDA backends it adds MORE SPECIFIC methods of the hot-path operators, so that
+#   A * x, mul!(y, A, x), transpose(A) * x, dot(x, y), norm(x)
+# run in hand-written sm_100a kernels with an NCCL halo exchange instead of the CPU-staged MPI path of
+# src/vectors.jl:394-463 and the one-thread-per-row KernelAbstractions kernel of src/sparse.jl:2055-2084.
+# Everything else of the package (constructors, plan construction with MPI, caches, the CPU backends) is untouched.
+module HPCLinearAlgebraB200Ext
+
+using HPCLinearAlgebra
+using CUDA
+using MPI
+using LinearAlgebra
+using HPCLinearAlgebra: HPCBackend, HPCVector, HPCSparseMatrix, VectorPlan, DeviceCUDA, CommMPI, CommSerial,
+                        comm_rank, comm_size, get_vector_plan, _ensure_hash, compute_partition_hash
+
+const libhpcla = get(ENV, "HPCLA_B200_LIB", "libhpcla_b200.so")
+
+const CuB{T,Ti,C,S} = HPCBackend{T,Ti,DeviceCUDA,C,S}
+
+_dtype(::Type{Float32}) = Cint(0)      # HPCLA_F32
+_dtype(::Type{Float64}) = Cint(1)      # HPCLA_F64
+_dtype(::Type{ComplexF64}) = Cint(2)   # HPCLA_C128
+_itype(::Type{Int32}) = Cint(0)        # HPCLA_I32
+_itype(::Type{Int64}) = Cint(1)        # HPCLA_I64
+
+function _check(status::Cint, what::AbstractString)
+    # same convention as the cuDSS / NCCL wrappers of ext/HPCLinearAlgebraCUDAExt.jl:247-251, 388-402
+    status == 0 || error("$what failed with status $status: " * unsafe_string(@ccall libhpcla.hpcla_last_error()::Cstring))
+    return nothing
+end
+
+_dptr(a::CuArray) = reinterpret(Ptr{Cvoid}, pointer(a))          # cf. ext/HPCLinearAlgebraCUDAExt.jl:665-669
+_stream() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)         # run on the caller's task-local stream
+
+# ---------------------------------------------------------------------------------------------------------------
+# context: one per (MPI communicator, device); the NCCL bootstrap is the reference's own
+# (ext/HPCLinearAlgebraCUDAExt.jl:411-443): rank 0 creates the id, MPI.Bcast! ships the 128 bytes.
+# Never destroyed (ext:384-386: destroying NCCL communicators from finalizers desynchronises ranks).
+# ---------------------------------------------------------------------------------------------------------------
+const _contexts = Dict{Any,Ptr{Cvoid}}()
+
+function _context(backend::CuB)
+    comm = backend.comm
+    key = comm isa CommMPI ? comm.comm.val : :serial
+    get!(_contexts, key) do
+        rank, nranks = comm_rank(comm), comm_size(comm)
+        dev = rank % length(CUDA.devices())                        # ext:611-613
+        CUDA.device!(dev)
+        ctx = Ref{Ptr{Cvoid}}(C_NULL)
+        _check(@ccall(libhpcla.hpcla_ctx_create(dev::Cint, rank::Cint, nranks::Cint, ctx::Ptr{Ptr{Cvoid}})::Cint), "hpcla_ctx_create")
+        if comm isa CommMPI && nranks > 1
+            id = zeros(UInt8, 128)
+            rank == 0 && _check(@ccall(libhpcla.hpcla_nccl_unique_id(id::Ptr{UInt8})::Cint), "hpcla_nccl_unique_id")
+            MPI.Bcast!(id, 0, comm.comm)
+            _check(@ccall(libhpcla.hpcla_ctx_init_nccl(ctx[]::Ptr{Cvoid}, id::Ptr{UInt8})::Cint), "hpcla_ctx_init_nccl")
+        end
+        ctx[]
+    end
+end
+
+# ---------------------------------------------------------------------------------------------------------------
+# side cache of device-derived state (HPCSparseMatrix has no spare field and HPCVector is immutable, SURVEY §8b):
+# keyed like the reference's plan cache (src/sparse.jl:1994) plus the identity of A.nzval; wiped with the plans.
+# ---------------------------------------------------------------------------------------------------------------
+mutable struct BoundOp
+    csr::Ptr{Cvoid}
+    plan::Ptr{Cvoid}
+    op::Ptr{Cvoid}
+    roots::Any   # keeps the borrowed arrays alive for the lifetime of the handles (cf. ext:549-551)
+end
+const _bound = Dict{Any,BoundOp}()
+
+function _bind(A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T}, plan::VectorPlan{T,Ti}) where {T,Ti,B<:CuB}
+    key = (_ensure_hash(A), x.structural_hash, T, Ti, objectid(A.nzval))
+    get!(_bound, key) do
+        ctx = _context(A.backend)
+        nnz = Int64(length(A.nzval))
+        csr = Ref{Ptr{Cvoid}}(C_NULL)
+        _check(@ccall(libhpcla.hpcla_csr_create(ctx::Ptr{Cvoid}, _dtype(T)::Cint, _itype(Ti)::Cint, Int64(A.nrows_local)::Int64,
+                  Int64(A.ncols_compressed)::Int64, nnz::Int64, _dptr(A.rowptr_target)::Ptr{Cvoid}, _dptr(A.colval_target)::Ptr{Cvoid},
+                  _dptr(A.nzval)::Ptr{Cvoid}, csr::Ptr{Ptr{Cvoid}})::Cint), "hpcla_csr_create")
+        # hand over the VectorPlan the reference already built with MPI (src/sparse.jl:1875-1984): no second protocol
+        sidx = [pointer(v) for v in plan.send_indices]; slen = Int64[length(v) for v in plan.send_indices]
+        rprm = [pointer(v) for v in plan.recv_perm];    rlen = Int64[length(v) for v in plan.recv_perm]
+        ph = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve plan begin
+            _check(@ccall(libhpcla.hpcla_plan_import(comm_rank(A.backend.comm)::Cint, comm_size(A.backend.comm)::Cint, _itype(Ti)::Cint,
+                      Int64(length(plan.gathered))::Int64, Int64(length(x.v))::Int64,
+                      Int64(length(plan.send_rank_ids))::Int64, Int64.(plan.send_rank_ids)::Ptr{Int64}, slen::Ptr{Int64}, sidx::Ptr{Ptr{Cvoid}},
+                      Int64(length(plan.recv_rank_ids))::Int64, Int64.(plan.recv_rank_ids)::Ptr{Int64}, rlen::Ptr{Int64}, rprm::Ptr{Ptr{Cvoid}},
+                      Int64(length(plan.local_src_indices))::Int64, plan.local_src_indices::Ptr{Cvoid}, plan.local_dst_indices::Ptr{Cvoid},
+                      ph::Ptr{Ptr{Cvoid}})::Cint), "hpcla_plan_import")
+        end
+        op = Ref{Ptr{Cvoid}}(C_NULL)
+        _check(@ccall(libhpcla.hpcla_spmv_create(ctx::Ptr{Cvoid}, csr[]::Ptr{Cvoid}, ph[]::Ptr{Cvoid}, Int64(length(x.v))::Int64,
+                  op::Ptr{Ptr{Cvoid}})::Cint), "hpcla_spmv_create")
+        BoundOp(csr[], ph[], op[], (A.rowptr_target, A.colval_target, A.nzval))
+    end
+end
+
+function _multiply!(y_local::CuVector{T}, A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T}) where {T,Ti,B<:CuB}
+    plan = get_vector_plan(A, x)                                   # memoised, src/sparse.jl:1992-2001
+    b = _bind(A, x, plan)
+    GC.@preserve x y_local begin
+        _check(@ccall(libhpcla.hpcla_spmv_run(b.op::Ptr{Cvoid}, _dptr(x.v)::Ptr{Cvoid}, _dptr(y_local)::Ptr{Cvoid}, _stream()::Ptr{Cvoid})::Cint),
+               "hpcla_spmv_run")
+    end
+    return plan
+end
+
+# --- Base.:*(A, x): replaces src/sparse.jl:2096-2128 for CUDA backends -------------------------------------------
+function Base.:*(A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T,B}) where {T,Ti,B<:CuB}
+    y_local = CUDA.zeros(T, A.nrows_local)
+    plan = _multiply!(y_local, A, x)
+    if plan.result_partition_hash === nothing                       # src/sparse.jl:2103-2106
+        plan.result_partition_hash = compute_partition_hash(A.row_partition)
+        plan.result_partition = copy(A.row_partition)
+    end
+    return HPCVector{T,B}(plan.result_partition_hash, plan.result_partition, y_local, A.backend)
+end
+
+# --- mul!(y, A, x): replaces src/sparse.jl:2019-2037 (which multiplies on the CPU) ---------------------------------
+function LinearAlgebra.mul!(y::HPCVector{T,B}, A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T,B}) where {T,Ti,B<:CuB}
+    _multiply!(y.v, A, x)
+    return y
+end
+
+# --- transpose(A) * x: src/sparse.jl:2375-2379 already materialises and caches A^T and calls A_transposed * x, which
+#     now dispatches to the method above; nothing to override.  (The one-time TransposePlan stays the reference's.)
+
+# --- execute_plan!: replaces src/vectors.jl:394-463 when somebody asks for `gathered` itself ----------------------
+#     (needs the matrix the plan belongs to; exposed as a helper rather than an override of the 2-argument method)
+function gather!(A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T,B}) where {T,Ti,B<:CuB}
+    plan = get_vector_plan(A, x)
+    b = _bind(A, x, plan)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(@ccall(libhpcla.hpcla_spmv_gather(b.op::Ptr{Cvoid}, _dptr(x.v)::Ptr{Cvoid}, _stream()::Ptr{Cvoid}, out::Ptr{Ptr{Cvoid}})::Cint), "hpcla_spmv_gather")
+    return unsafe_wrap(CuArray, reinterpret(CuPtr{T}, out[]), length(plan.gathered))
+end
+
+# --- dot / norm: replace src/vectors.jl:798-812, 758-766 (CUBLAS + MPI.Allreduce of a host scalar) -----------------
+function LinearAlgebra.dot(x::HPCVector{T,B}, y::HPCVector{T,B}) where {T,B<:CuB}
+    x.structural_hash == y.structural_hash || return invoke(LinearAlgebra.dot, Tuple{HPCVector{T},HPCVector{T}}, x, y)
+    r = Ref{T}()
+    _check(@ccall(libhpcla.hpcla_dot(_context(x.backend)::Ptr{Cvoid}, _dtype(T)::Cint, Int64(length(x.v))::Int64, _dptr(x.v)::Ptr{Cvoid},
+              _dptr(y.v)::Ptr{Cvoid}, r::Ptr{Cvoid}, _stream()::Ptr{Cvoid})::Cint), "hpcla_dot")
+    return r[]
+end
+
+function LinearAlgebra.norm(x::HPCVector{T,B}, p::Real=2) where {T,B<:CuB}
+    p == 2 || return invoke(LinearAlgebra.norm, Tuple{HPCVector{T},Real}, x, p)
+    r = Ref{real(T)}()
+    _check(@ccall(libhpcla.hpcla_nrm2(_context(x.backend)::Ptr{Cvoid}, _dtype(T)::Cint, Int64(length(x.v))::Int64, _dptr(x.v)::Ptr{Cvoid},
+              r::Ptr{Cvoid}, _stream()::Ptr{Cvoid})::Cint), "hpcla_nrm2")
+    return r[]
+end
+
+# --- cache hygiene: clear_plan_cache!() (src/HPCLinearAlgebra.jl:181-201) must also drop the device state ----------
+function clear_bound!()
+    for b in values(_bound)
+        @ccall libhpcla.hpcla_spmv_destroy(b.op::Ptr{Cvoid})::Cvoid
+        @ccall libhpcla.hpcla_plan_destroy(b.plan::Ptr{Cvoid})::Cvoid
+        @ccall libhpcla.hpcla_csr_destroy(b.csr::Ptr{Cvoid})::Cvoid
+    end
+    empty!(_bound)
+end
+
+end # module

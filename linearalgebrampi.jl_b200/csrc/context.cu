@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -269,8 +270,8 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     if (!ctx || !out || nrows < 0 || ncc < 0 || nnz < 0 || !d_rowptr) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: bad arguments");
     if (!dtype_size(dtype) || !itype_size(itype)) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: unknown dtype/itype");
     if (nnz > 0 && (!d_colval || !d_nzval)) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: null colval/nzval");
-    if (((uintptr_t)d_colval & 15) || ((uintptr_t)d_nzval & 15))
-        return fail(HPCLA_ERR_ARG, "hpcla_csr_create: colval and nzval must be 16-byte aligned (128-bit loads)");
+    if (((uintptr_t)d_colval & 15) || ((uintptr_t)d_nzval & 15) || ((uintptr_t)d_rowptr & 15))
+        return fail(HPCLA_ERR_ARG, "hpcla_csr_create: rowptr, colval and nzval must be 16-byte aligned (128-bit loads / bulk copies)");
     if (itype == HPCLA_I32 && nnz >= (i64)INT32_MAX) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: nnz does not fit Int32 row pointers");
     int rc = set_device(ctx);
     if (rc) return rc;
@@ -285,6 +286,18 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     A->d_colval = d_colval;
     A->d_nzval = d_nzval;
     A->shape = tile_shape(dtype);
+    if (A->shape.variant == 2 && nrows > 0) {
+        // short rows: one lane per row, so size the window to about one row per thread (one pass over the rows)
+        const double avg = (double)nnz / (double)nrows;
+        if (avg > 0 && avg <= 16.0) {
+            int w = ((int)(A->shape.threads * avg)) & ~3;
+            if (w >= 256 && w < A->shape.window) A->shape.window = w;
+        }
+    }
+    if (const char* e = getenv("HPCLA_TILE_WINDOW")) {
+        int w = atoi(e) & ~3;
+        if (w >= 64 && w <= A->shape.smem_elems - 8) A->shape.window = w;
+    }
     A->ntiles = nnz / A->shape.window + 1;
     if (A->ntiles >= (i64)INT32_MAX) {
         delete A;
@@ -591,6 +604,7 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
     L.nzval = A->d_nzval;
     L.nrows = A->nrows;
     L.nnz = A->nnz;
+    L.shape = A->shape;
     L.tiles = A->d_tiles;
     L.x_own = op->x_in_place ? (const void*)((const char*)d_x + (size_t)(op->own_src0 - 1) * es)
                              : (const void*)((const char*)op->d_gathered + (size_t)(op->own_lo - 1) * es);

@@ -18,7 +18,8 @@ struct TileShape {
     int threads;     // CTA size
     int chunk;       // nonzeros staged per round = threads * groups * 4
     int window;      // nonzeros per tile window = chunk - 64
-    int smem_elems;  // products that fit in shared memory = chunk + 512
+    int smem_elems;  // staged nonzeros that fit in shared memory = chunk + slack
+    int variant;     // 1 = LDG + staged products, 2 = TMA-staged operands
 };
 TileShape tile_shape(int dtype);
 
@@ -28,6 +29,7 @@ struct SpmvLaunch {
     const void* colval;
     const void* nzval;
     i64 nrows, nnz;
+    TileShape shape;        // as fixed when the tile table was built
     const TileDesc* tiles;  // [ntiles+1]
     const int* tile_list;   // nullptr: tiles 0..n_launch-1
     int n_launch;

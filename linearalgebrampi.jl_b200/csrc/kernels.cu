@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "device.h"
 
@@ -103,6 +104,12 @@ __device__ __forceinline__ void st_y(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_y(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_y(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
 
+// per element type: CTA size, 4-nonzero groups per lane and round (variant 1), resident CTAs per SM aimed at (variant 2)
+template <class T> struct TileCfg;
+template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2, MIN_CTAS = 8; };
+template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2, MIN_CTAS = 7; };
+template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1, MIN_CTAS = 5; };
+
 // x addressing: own columns are read straight from x.v (no local copy into `gathered`), ghosts from `gathered`.
 template <class T>
 struct XView {
@@ -159,7 +166,7 @@ __device__ __forceinline__ void reduce_rows(const T* prod, const Ti* __restrict_
 
 template <class T, class Ti, int THREADS, int GROUPS, bool GHOST>
 __global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti> a, int smem_elems) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* prod = reinterpret_cast<T*>(smem_raw);
     constexpr int CHUNK = THREADS * GROUPS * 4;
     const int tid = threadIdx.x;
@@ -227,6 +234,178 @@ __global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti
         for (i64 r = r0 + warp; r < r1; r += THREADS / 32) {
             const i64 b = (i64)__ldg(a.rowptr + r) - 1, en = (i64)__ldg(a.rowptr + r + 1) - 1;
             if (en - b > a.long_threshold) continue;  // left to the split kernels
+            T acc = el_zero(T());
+            for (i64 k = b + lane; k < en; k += 32) {
+                const Ti c = ld_stream(a.colval + k);
+                acc = el_add(acc, el_mul(ld_stream(a.nzval + k), x_at<GHOST, T, Ti>(a.xv, c)));
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+            if (lane == 0) st_y(a.y + r, acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Variant 2 (default): TMA-staged tiles.
+// One elected thread issues three bulk asynchronous copies (cp.async.bulk, the 1-D TMA path: global -> shared through
+// L2, bypassing the LSU/L1 wavefront pipeline that bounded variant 1, evict-first in L2) for the tile's slice of
+// colval, nzval and rowptr, completing on an mbarrier.  Then G lanes per row walk the staged row: with one lane per
+// row, consecutive lanes handle consecutive ROWS, so for banded / stencil matrices the x gathers of one warp
+// instruction hit consecutive addresses (coalesced), and the row is summed left to right exactly like the reference.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+// rows of a staged tile: G lanes per row, operands from shared memory, x through the read-only path
+template <class T, class Ti, int THREADS, int G, bool GHOST, bool RP_SMEM>
+__device__ __forceinline__ void rows_from_staged(const Ti* scol, const T* sval, const Ti* srp, const Ti* __restrict__ rowptr, const XView<T>& xv,
+                                                 T* __restrict__ y, i64 r0, i64 r1, i64 rp0, i64 s4, int tid) {
+    constexpr int RPP = THREADS / G;
+    const int lane = tid % G;
+    for (i64 base = r0; base < r1; base += RPP) {
+        const i64 r = base + tid / G;
+        const bool valid = r < r1;
+        T acc = el_zero(T());
+        if (valid) {
+            int b, e;
+            if (RP_SMEM) {
+                b = (int)((i64)srp[r - rp0] - 1 - s4);
+                e = (int)((i64)srp[r - rp0 + 1] - 1 - s4);
+            } else {
+                b = (int)((i64)__ldg(rowptr + r) - 1 - s4);
+                e = (int)((i64)__ldg(rowptr + r + 1) - 1 - s4);
+            }
+            if (G == 1) {
+                // independent loads first (4 at a time), then the adds in the reference's order
+                int k = b;
+                for (; k + 4 <= e; k += 4) {
+                    T p[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) p[u] = el_mul(sval[k + u], x_at<GHOST, T, Ti>(xv, scol[k + u]));
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
+                }
+                for (; k < e; ++k) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
+            } else {
+                for (int k = b + lane; k < e; k += G) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
+            }
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+        }
+        if (valid && lane == 0) st_y(y + r, acc);
+    }
+}
+
+template <class T, class Ti, int THREADS, bool GHOST, bool RP_SMEM>
+__device__ __forceinline__ void dispatch_rows(int G, const Ti* scol, const T* sval, const Ti* srp, const Ti* rowptr, const XView<T>& xv, T* y, i64 r0,
+                                              i64 r1, i64 rp0, i64 s4, int tid) {
+    switch (G) {
+        case 1: rows_from_staged<T, Ti, THREADS, 1, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
+        case 2: rows_from_staged<T, Ti, THREADS, 2, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
+        case 4: rows_from_staged<T, Ti, THREADS, 4, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
+        case 8: rows_from_staged<T, Ti, THREADS, 8, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
+        case 16: rows_from_staged<T, Ti, THREADS, 16, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
+        default: rows_from_staged<T, Ti, THREADS, 32, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
+    }
+}
+
+constexpr int TMA_RP_CAP = 640;  // staged row pointers per tile (tiles with more rows read rowptr from global memory)
+
+template <class T, class Ti, int THREADS, bool GHOST>
+__global__ void __launch_bounds__(THREADS, TileCfg<T>::MIN_CTAS) spmv_tile_tma_kernel(const TileArgs<T, Ti> a, int smem_elems, i64 rowptr_len) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    Ti* srp = reinterpret_cast<Ti*>(smem_raw + 16);
+    Ti* scol = reinterpret_cast<Ti*>(smem_raw + 16 + sizeof(Ti) * TMA_RP_CAP);
+    T* sval = reinterpret_cast<T*>(smem_raw + 16 + sizeof(Ti) * TMA_RP_CAP + sizeof(Ti) * (size_t)smem_elems);
+    const int tid = threadIdx.x;
+    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
+    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
+    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
+    const i64 r0 = d0.x, r1 = d1.x;
+    if (r1 <= r0) return;
+    const i64 s = d0.y, e = d1.y;
+    const i64 s4 = s & ~(i64)3;
+    const i64 n = e - s4;
+    if (n <= (i64)smem_elems) {
+        // element ranges to stage (16-byte granular bulk copies; the <= 3 trailing elements that a 16-byte copy would
+        // read past the end of the arrays are fetched with ordinary loads)
+        const i64 avail = a.nnz_total - s4;
+        const int n_need = (int)n;
+        const int n_bulk = (int)(((n + 3) & ~(i64)3) <= avail ? ((n + 3) & ~(i64)3) : (avail & ~(i64)3));
+        const i64 rp0 = r0 & ~(i64)3;
+        const i64 rp_need = r1 + 1 - rp0;  // entries rp0 .. r1
+        const bool rp_smem = rp_need <= TMA_RP_CAP;
+        const i64 rp_avail = rowptr_len - rp0;
+        const int rp_bulk = rp_smem ? (int)(((rp_need + 3) & ~(i64)3) <= rp_avail ? ((rp_need + 3) & ~(i64)3) : (rp_avail & ~(i64)3)) : 0;
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const uint64_t pol = l2_evict_first_policy();
+            const uint32_t bytes = (uint32_t)n_bulk * (uint32_t)(sizeof(Ti) + sizeof(T)) + (uint32_t)rp_bulk * (uint32_t)sizeof(Ti);
+            mbar_expect_tx(bar, bytes);
+            if (n_bulk > 0) {
+                bulk_g2s(scol, a.colval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(Ti), bar, pol);
+                bulk_g2s(sval, a.nzval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(T), bar, pol);
+            }
+            if (rp_bulk > 0) bulk_g2s(srp, a.rowptr + rp0, (uint32_t)rp_bulk * (uint32_t)sizeof(Ti), bar, pol);
+        }
+        // tails (at most 3 elements each; only the last tile of the matrix)
+        if (n_bulk < n_need)
+            for (int k = n_bulk + tid; k < n_need; k += THREADS) {
+                scol[k] = a.colval[s4 + k];
+                sval[k] = a.nzval[s4 + k];
+            }
+        if (rp_smem && rp_bulk < rp_need)
+            for (int k = rp_bulk + tid; k < (int)rp_need; k += THREADS) srp[k] = a.rowptr[rp0 + k];
+        const bool tails = (n_bulk < n_need) || (rp_smem && rp_bulk < rp_need);
+        mbar_wait(bar, 0);
+        if (tails) __syncthreads();
+        // lanes per row: fill the CTA (rows * G ~ THREADS) without exceeding a quarter of the mean row length
+        const i64 nrows_t = r1 - r0;
+        const i64 avg = (e - s) / nrows_t;
+        int G = 1;
+        while (G < 32 && nrows_t * (2 * G) <= THREADS && avg >= 8 * G) G *= 2;
+        while (G < 32 && avg > 32 * G) G *= 2;
+        if (rp_smem) dispatch_rows<T, Ti, THREADS, GHOST, true>(G, scol, sval, srp, a.rowptr, a.xv, a.y, r0, r1, rp0, s4, tid);
+        else dispatch_rows<T, Ti, THREADS, GHOST, false>(G, scol, sval, srp, a.rowptr, a.xv, a.y, r0, r1, rp0, s4, tid);
+    } else {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (i64 r = r0 + warp; r < r1; r += THREADS / 32) {
+            const i64 b = (i64)__ldg(a.rowptr + r) - 1, en = (i64)__ldg(a.rowptr + r + 1) - 1;
+            if (en - b > a.long_threshold) continue;
             T acc = el_zero(T());
             for (i64 k = b + lane; k < en; k += 32) {
                 const Ti c = ld_stream(a.colval + k);
@@ -481,18 +660,16 @@ __global__ void cg_update_p_kernel(i64 n, const T* __restrict__ r, T* __restrict
 // ==================================================================================================================
 // host-side launchers
 // ==================================================================================================================
-template <class T> struct TileCfg;
-template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2; };
-template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2; };
-template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1; };
 
+int spmv_variant();
 template <class T>
 static TileShape shape_of() {
     TileShape s;
     s.threads = TileCfg<T>::THREADS;
     s.chunk = TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4;
+    s.variant = spmv_variant();
     s.window = s.chunk - 64;
-    s.smem_elems = s.chunk + 512;
+    s.smem_elems = s.chunk + (s.variant == 1 ? 512 : 256);
     return s;
 }
 TileShape tile_shape(int dtype) {
@@ -538,11 +715,16 @@ static XView<T> make_xview(const void* x_own, const void* gathered, i64 own_lo, 
     return v;
 }
 
+int spmv_variant() {
+    const char* e = getenv("HPCLA_SPMV_VARIANT");
+    return (e && e[0] == '1') ? 1 : 2;  // 1 = LDG + staged products, 2 = TMA-staged operands (default)
+}
+
 template <class T, class Ti>
 static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
     if (L.n_launch <= 0) return cudaSuccess;
     constexpr int THREADS = TileCfg<T>::THREADS, GROUPS = TileCfg<T>::GROUPS;
-    const TileShape sh = shape_of<T>();
+    const TileShape& sh = L.shape;
     TileArgs<T, Ti> a;
     a.rowptr = (const Ti*)L.rowptr;
     a.colval = (const Ti*)L.colval;
@@ -554,9 +736,32 @@ static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
     a.nnz_total = L.nnz;
     a.long_threshold = L.long_threshold;
     a.safe_col = L.own_n > 0 ? L.own_lo : 1;
-    const size_t smem = (size_t)sh.smem_elems * sizeof(T);
-    if (L.has_ghost) spmv_tile_kernel<T, Ti, THREADS, GROUPS, true><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
-    else spmv_tile_kernel<T, Ti, THREADS, GROUPS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
+    if (sh.variant == 1) {
+        const size_t smem = (size_t)sh.smem_elems * sizeof(T);
+        if (L.has_ghost) spmv_tile_kernel<T, Ti, THREADS, GROUPS, true><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
+        else spmv_tile_kernel<T, Ti, THREADS, GROUPS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
+        return cudaGetLastError();
+    }
+    const size_t smem = 16 + sizeof(Ti) * TMA_RP_CAP + (size_t)sh.smem_elems * (sizeof(Ti) + sizeof(T));
+    static bool configured[2][64] = {};  // per instantiation, per device: function attributes are per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& done = configured[L.has_ghost ? 1 : 0][dev & 63];
+    if (L.has_ghost) {
+        if (!done) {
+            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            done = true;
+        }
+        spmv_tile_tma_kernel<T, Ti, THREADS, true><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems, L.nrows + 1);
+    } else {
+        if (!done) {
+            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            done = true;
+        }
+        spmv_tile_tma_kernel<T, Ti, THREADS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems, L.nrows + 1);
+    }
     return cudaGetLastError();
 }
 

@@ -1,0 +1,92 @@
+"""Multi-process NCCL worker for tests/test_gpu_nccl.py (one process per GPU, run under torch.distributed.run).
+Checks the real grouped ncclSend/ncclRecv halo exchange against the oracle on every rank."""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+import hpcla_b200 as la
+from oracle import oracle as orc
+
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12, np.dtype(np.complex128): 1e-12}
+
+
+def relerr(y, ref):
+    return np.linalg.norm(np.asarray(y) - np.asarray(ref)) / max(np.linalg.norm(np.asarray(ref)), 1e-300)
+
+
+def main():
+    local_rank = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rank, P = dist.get_rank(), dist.get_world_size()
+    comm = la.CommMPI()
+    rng = np.random.default_rng(2024)  # identical on all ranks ("test matrices must be deterministic")
+    S = la.synth
+    # 1. stencils, all element types: A*x, mul!, transpose(A)*x, gathered
+    for kind, N, T, Ti in [(1, 40, np.float64, np.int32), (1, 31, np.float32, np.int64), (2, 18, np.complex128, np.int32), (0, 300, np.float64, np.int64)]:
+        b = la.backend_cuda_mpi(T, Ti, comm=comm, device=local_rank)
+        n = S.stencil_rows(kind, N if kind else (N, N))
+        grid = N if kind else (N, N)
+        A = S.stencil_matrix(kind, grid, b)
+        x = S.vector(n, b)
+        y = A * x
+        y2 = la.mul(la.HPCVector.zeros(b, n), A, x)
+        yT = la.transpose(A) * x
+        g = la.execute_plan(la.get_vector_plan(A, x), A, x)
+        torch.cuda.synchronize()
+        rp, c, v = S.stencil_local(kind, grid, 0, n, T, Ti)
+        G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+        olocs = orc.distribute(G, P, itype="i32" if Ti == np.int32 else "i64")
+        xh = S.vector_local(T, S.X_SEED, 0, n)
+        ref = orc.matvec(olocs, xh)
+        refT = orc.matvec(orc.transpose(olocs), xh)
+        assert relerr(y.to_global(), ref) <= TOL[np.dtype(T)], ("A*x", kind, relerr(y.to_global(), ref))
+        assert relerr(y2.to_global(), ref) <= TOL[np.dtype(T)]
+        assert relerr(yT.to_global(), refT) <= TOL[np.dtype(T)]
+        W = orc.PlanWorld(olocs, orc.uniform_partition(n, P))
+        assert np.array_equal(g.cpu().numpy(), W.execute(orc.split_vector(xh, orc.uniform_partition(n, P)))[rank])
+        W.close()
+        info = la.spmv_info(A, x)
+        assert info["x_in_place"] == 1 and info["sends_contiguous"] == 1 and info["boundary_tiles"] > 0
+        if kind in (0, 1) and T == np.float64:
+            assert np.array_equal(y.to_global(), ref)
+    # 2. random ragged matrix: non-contiguous sends (pack kernel), foreign x partition, empty rows
+    for T, Ti in [(np.float64, np.int32), (np.complex128, np.int64)]:
+        b = la.backend_cuda_mpi(T, Ti, comm=comm, device=local_rank)
+        m, n = 2000, 1500
+        R = sp.random(m, n, density=0.01, random_state=np.random.default_rng(5), format="csr")
+        R.data = np.random.default_rng(6).uniform(-1, 1, R.nnz)
+        R = R.astype(T)
+        xh = np.random.default_rng(7).uniform(-1, 1, n).astype(T)
+        xp = np.concatenate([[1], np.sort(np.random.default_rng(8).integers(1, n + 1, size=P - 1)) , [n + 1]]).astype(np.int64)
+        A = la.HPCSparseMatrix.from_global(R, b)
+        x = la.HPCVector.from_global(xh, b, partition=xp)
+        y = A * x
+        olocs = orc.distribute(R, P, itype="i32" if Ti == np.int32 else "i64")
+        assert relerr(y.to_global(), orc.matvec(olocs, xh, xp)) <= TOL[np.dtype(T)]
+        assert la.spmv_info(A, x)["sends_contiguous"] == 0
+    # 3. reductions + CG over NCCL
+    b = la.backend_cuda_mpi(np.float64, np.int32, comm=comm, device=local_rank)
+    N = 20
+    n = N**3
+    A = S.stencil_matrix(1, N, b)
+    x = S.vector(n, b)
+    xh = S.vector_local(np.float64, S.X_SEED, 0, n)
+    assert abs(la.dot(x, x) - np.dot(xh, xh)) <= 1e-10 * n and abs(la.norm(x) - np.linalg.norm(xh)) <= 1e-10
+    rp, c, v = S.stencil_local(1, N, 0, n, np.float64, np.int32)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    bh = G @ np.ones(n)
+    sol, hist = la.cg(A, la.HPCVector.from_global(bh, b), 30)
+    xo, ho = orc.cg(orc.distribute(G, 1, itype="i32"), bh, 30)
+    assert relerr(sol.to_global(), xo) <= 1e-9 and np.allclose(hist, ho, rtol=1e-8)
+    dist.barrier()
+    print("NCCL_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
