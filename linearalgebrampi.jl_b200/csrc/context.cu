@@ -661,9 +661,10 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     }
     SpmvLaunch L;
     fill_launch(op, L, d_x, d_y);
-    if (op->has_ghost) {  // interior tiles: only own columns, run while the halo is in flight
+    if (op->has_ghost) {  // interior tiles: only own columns (so the ghost-free kernel), run while the halo is in flight
         L.tile_list = op->d_list_int;
         L.n_launch = op->n_int;
+        L.has_ghost = false;
     } else {
         L.tile_list = nullptr;
         L.n_launch = (int)op->csr->ntiles;

@@ -106,9 +106,25 @@ __device__ __forceinline__ void st_y(cplx* p, cplx v) { __stcs(reinterpret_cast<
 
 // per element type: CTA size, 4-nonzero groups per lane and round (variant 1), resident CTAs per SM aimed at (variant 2)
 template <class T> struct TileCfg;
-template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2, MIN_CTAS = 8; };
-template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2, MIN_CTAS = 7; };
-template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1, MIN_CTAS = 5; };
+template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2; };
+template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2; };
+template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1; };
+constexpr int TMA_RP_CAP = 640;  // staged row pointers per tile (tiles with more rows read rowptr from global memory)
+constexpr int TMA_SLACK = 256;   // staged nonzeros beyond the chunk (rows may run past the window)
+// shared memory of one variant-2 CTA and the resident CTAs per SM it allows (227 KB usable, at most 2048 threads)
+template <class T, class Ti>
+constexpr size_t tma_smem_bytes() {
+    return 16 + 32 * sizeof(T) + sizeof(Ti) * TMA_RP_CAP + (size_t)(TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4 + TMA_SLACK) * (sizeof(Ti) + sizeof(T));
+}
+template <class T> struct RegCap { static constexpr int CTAS = 8; };       // 32 registers per thread
+template <> struct RegCap<double> { static constexpr int CTAS = 7; };      // 36
+template <> struct RegCap<cplx> { static constexpr int CTAS = 5; };        // 48 (16-byte values)
+template <class T, class Ti, bool GHOST>
+constexpr int tma_min_ctas() {
+    int by_smem = (int)((227 * 1024) / (tma_smem_bytes<T, Ti>() + 1024));
+    int cap = RegCap<T>::CTAS - (GHOST ? 1 : 0);
+    return by_smem < cap ? by_smem : cap;
+}
 
 // x addressing: own columns are read straight from x.v (no local copy into `gathered`), ghosts from `gathered`.
 template <class T>
@@ -283,145 +299,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
-// rows of a staged tile: G lanes per row, operands from shared memory, x through the read-only path
-template <class T, class Ti, int THREADS, int G, bool GHOST, bool RP_SMEM>
-__device__ __forceinline__ void rows_from_staged(const Ti* scol, const T* sval, const Ti* srp, const Ti* __restrict__ rowptr, const XView<T>& xv,
-                                                 T* __restrict__ y, i64 r0, i64 r1, i64 rp0, i64 s4, int tid) {
-    constexpr int RPP = THREADS / G;
-    const int lane = tid % G;
-    for (i64 base = r0; base < r1; base += RPP) {
-        const i64 r = base + tid / G;
-        const bool valid = r < r1;
-        T acc = el_zero(T());
-        if (valid) {
-            int b, e;
-            if (RP_SMEM) {
-                b = (int)((i64)srp[r - rp0] - 1 - s4);
-                e = (int)((i64)srp[r - rp0 + 1] - 1 - s4);
-            } else {
-                b = (int)((i64)__ldg(rowptr + r) - 1 - s4);
-                e = (int)((i64)__ldg(rowptr + r + 1) - 1 - s4);
-            }
-            if (G == 1) {
-                // independent loads first (4 at a time), then the adds in the reference's order
-                int k = b;
-                for (; k + 4 <= e; k += 4) {
-                    T p[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) p[u] = el_mul(sval[k + u], x_at<GHOST, T, Ti>(xv, scol[k + u]));
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
-                }
-                for (; k < e; ++k) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
-            } else {
-                for (int k = b + lane; k < e; k += G) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
-            }
-        }
-        if (G > 1) {
-#pragma unroll
-            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
-        }
-        if (valid && lane == 0) st_y(y + r, acc);
-    }
-}
-
-template <class T, class Ti, int THREADS, bool GHOST, bool RP_SMEM>
-__device__ __forceinline__ void dispatch_rows(int G, const Ti* scol, const T* sval, const Ti* srp, const Ti* rowptr, const XView<T>& xv, T* y, i64 r0,
-                                              i64 r1, i64 rp0, i64 s4, int tid) {
-    switch (G) {
-        case 1: rows_from_staged<T, Ti, THREADS, 1, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
-        case 2: rows_from_staged<T, Ti, THREADS, 2, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
-        case 4: rows_from_staged<T, Ti, THREADS, 4, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
-        case 8: rows_from_staged<T, Ti, THREADS, 8, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
-        case 16: rows_from_staged<T, Ti, THREADS, 16, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
-        default: rows_from_staged<T, Ti, THREADS, 32, GHOST, RP_SMEM>(scol, sval, srp, rowptr, xv, y, r0, r1, rp0, s4, tid); break;
-    }
-}
-
-constexpr int TMA_RP_CAP = 640;  // staged row pointers per tile (tiles with more rows read rowptr from global memory)
-
-template <class T, class Ti, int THREADS, bool GHOST>
-__global__ void __launch_bounds__(THREADS, TileCfg<T>::MIN_CTAS) spmv_tile_tma_kernel(const TileArgs<T, Ti> a, int smem_elems, i64 rowptr_len) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    Ti* srp = reinterpret_cast<Ti*>(smem_raw + 16);
-    Ti* scol = reinterpret_cast<Ti*>(smem_raw + 16 + sizeof(Ti) * TMA_RP_CAP);
-    T* sval = reinterpret_cast<T*>(smem_raw + 16 + sizeof(Ti) * TMA_RP_CAP + sizeof(Ti) * (size_t)smem_elems);
-    const int tid = threadIdx.x;
-    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
-    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
-    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
-    const i64 r0 = d0.x, r1 = d1.x;
-    if (r1 <= r0) return;
-    const i64 s = d0.y, e = d1.y;
-    const i64 s4 = s & ~(i64)3;
-    const i64 n = e - s4;
-    if (n <= (i64)smem_elems) {
-        // element ranges to stage (16-byte granular bulk copies; the <= 3 trailing elements that a 16-byte copy would
-        // read past the end of the arrays are fetched with ordinary loads)
-        const i64 avail = a.nnz_total - s4;
-        const int n_need = (int)n;
-        const int n_bulk = (int)(((n + 3) & ~(i64)3) <= avail ? ((n + 3) & ~(i64)3) : (avail & ~(i64)3));
-        const i64 rp0 = r0 & ~(i64)3;
-        const i64 rp_need = r1 + 1 - rp0;  // entries rp0 .. r1
-        const bool rp_smem = rp_need <= TMA_RP_CAP;
-        const i64 rp_avail = rowptr_len - rp0;
-        const int rp_bulk = rp_smem ? (int)(((rp_need + 3) & ~(i64)3) <= rp_avail ? ((rp_need + 3) & ~(i64)3) : (rp_avail & ~(i64)3)) : 0;
-        if (tid == 0) {
-            mbar_init(bar, 1);
-            mbar_fence_init();
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const uint64_t pol = l2_evict_first_policy();
-            const uint32_t bytes = (uint32_t)n_bulk * (uint32_t)(sizeof(Ti) + sizeof(T)) + (uint32_t)rp_bulk * (uint32_t)sizeof(Ti);
-            mbar_expect_tx(bar, bytes);
-            if (n_bulk > 0) {
-                bulk_g2s(scol, a.colval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(Ti), bar, pol);
-                bulk_g2s(sval, a.nzval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(T), bar, pol);
-            }
-            if (rp_bulk > 0) bulk_g2s(srp, a.rowptr + rp0, (uint32_t)rp_bulk * (uint32_t)sizeof(Ti), bar, pol);
-        }
-        // tails (at most 3 elements each; only the last tile of the matrix)
-        if (n_bulk < n_need)
-            for (int k = n_bulk + tid; k < n_need; k += THREADS) {
-                scol[k] = a.colval[s4 + k];
-                sval[k] = a.nzval[s4 + k];
-            }
-        if (rp_smem && rp_bulk < rp_need)
-            for (int k = rp_bulk + tid; k < (int)rp_need; k += THREADS) srp[k] = a.rowptr[rp0 + k];
-        const bool tails = (n_bulk < n_need) || (rp_smem && rp_bulk < rp_need);
-        mbar_wait(bar, 0);
-        if (tails) __syncthreads();
-        // lanes per row: fill the CTA (rows * G ~ THREADS) without exceeding a quarter of the mean row length
-        const i64 nrows_t = r1 - r0;
-        const i64 avg = (e - s) / nrows_t;
-        int G = 1;
-        while (G < 32 && nrows_t * (2 * G) <= THREADS && avg >= 8 * G) G *= 2;
-        while (G < 32 && avg > 32 * G) G *= 2;
-        if (rp_smem) dispatch_rows<T, Ti, THREADS, GHOST, true>(G, scol, sval, srp, a.rowptr, a.xv, a.y, r0, r1, rp0, s4, tid);
-        else dispatch_rows<T, Ti, THREADS, GHOST, false>(G, scol, sval, srp, a.rowptr, a.xv, a.y, r0, r1, rp0, s4, tid);
-    } else {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (i64 r = r0 + warp; r < r1; r += THREADS / 32) {
-            const i64 b = (i64)__ldg(a.rowptr + r) - 1, en = (i64)__ldg(a.rowptr + r + 1) - 1;
-            if (en - b > a.long_threshold) continue;
-            T acc = el_zero(T());
-            for (i64 k = b + lane; k < en; k += 32) {
-                const Ti c = ld_stream(a.colval + k);
-                acc = el_add(acc, el_mul(ld_stream(a.nzval + k), x_at<GHOST, T, Ti>(a.xv, c)));
-            }
-#pragma unroll
-            for (int m = 16; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
-            if (lane == 0) st_y(a.y + r, acc);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// very long rows ("merge-path split"): the row's nonzero range is cut into equal chunks, one CTA per chunk writes
-// one partial sum, a second kernel adds the partials of a row in chunk order.  Deterministic, no atomics.
-// ------------------------------------------------------------------------------------------------------------------
 template <class T>
 __device__ __forceinline__ T block_sum(T v, T* sh /* [32] */) {
 #pragma unroll
@@ -438,6 +315,197 @@ __device__ __forceinline__ T block_sum(T v, T* sh /* [32] */) {
     return r;  // valid in warp 0
 }
 
+// Mode A — row walk: G = 1 lane per row, operands read from shared memory, x gathered per row entry.  Consecutive lanes
+// own consecutive rows: on banded matrices a warp's gathers are coalesced; the sum runs left to right (reference order).
+template <class T, class Ti, int THREADS, bool GHOST>
+__device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const Ti* rp, i64 rp_off, const XView<T>& xv, T* __restrict__ y, i64 r0,
+                                          i64 r1, i64 s4, int tid) {
+    for (i64 r = r0 + tid; r < r1; r += THREADS) {
+        const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
+        const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
+        T acc = el_zero(T());
+        int k = b;
+        for (; k + 4 <= e; k += 4) {  // independent loads first (4 at a time), then the adds in the reference's order
+            T p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = el_mul(sval[k + u], x_at<GHOST, T, Ti>(xv, scol[k + u]));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
+        }
+        for (; k < e; ++k) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
+        st_y(y + r, acc);
+    }
+}
+
+// Mode B, step 2 — per-row sums of the staged products by G cooperating lanes (G = 1: reference order)
+template <class T, class Ti, int THREADS, int G>
+__device__ __forceinline__ void rows_sum(const T* prod, const Ti* rp, i64 rp_off, T* __restrict__ y, i64 r0, i64 r1, i64 s4, int tid) {
+    constexpr int RPP = THREADS / G;
+    const int lane = tid % G;
+    for (i64 base = r0; base < r1; base += RPP) {
+        const i64 r = base + tid / G;
+        const bool valid = r < r1;
+        T acc = el_zero(T());
+        if (valid) {
+            const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
+            const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
+            for (int k = b + lane; k < e; k += G) acc = el_add(acc, prod[k]);
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+        }
+        if (valid && lane == 0) st_y(y + r, acc);
+    }
+}
+
+__device__ __forceinline__ void ld4_shared(const int* p, int (&v)[4]) {
+    int4 t = *reinterpret_cast<const int4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void ld4_shared(const long long* p, long long (&v)[4]) {
+    longlong2 a = reinterpret_cast<const longlong2*>(p)[0], b = reinterpret_cast<const longlong2*>(p)[1];
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+__device__ __forceinline__ void ld4_shared(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+__device__ __forceinline__ void ld4_shared(const double* p, double (&v)[4]) {
+    double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+__device__ __forceinline__ void ld4_shared(const cplx* p, cplx (&v)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double2 t = reinterpret_cast<const double2*>(p)[k];
+        v[k] = cplx{t.x, t.y};
+    }
+}
+
+template <class T, class Ti, int THREADS, bool GHOST>
+__global__ void __launch_bounds__(THREADS, tma_min_ctas<T, Ti, GHOST>()) spmv_tile_tma_kernel(const TileArgs<T, Ti> a, int cap, i64 rowptr_len) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    T* red = reinterpret_cast<T*>(smem_raw + 16);  // [32] block-reduction scratch
+    Ti* srp = reinterpret_cast<Ti*>(smem_raw + 16 + 32 * sizeof(T));
+    Ti* scol = srp + TMA_RP_CAP;
+    T* sval = reinterpret_cast<T*>(scol + cap);
+    const int tid = threadIdx.x;
+    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
+    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
+    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
+    const i64 r0 = d0.x, r1 = d1.x;
+    if (r1 <= r0) return;
+    const i64 s = d0.y, e = d1.y;  // 0-based nonzero range of the tile's rows
+    const i64 s4 = s & ~(i64)3;    // 16-byte aligned for every element width
+    const i64 n_all = e - s4;
+    // Rows start inside the tile's window, so only the LAST row can run past it: everything up to `cap` elements is
+    // staged; an overrunning last row is finished from global memory by the whole CTA.
+    const bool overrun = n_all > (i64)cap;
+    const int n_st = overrun ? cap : (int)n_all;
+    const i64 avail = a.nnz_total - s4;
+    const int n_bulk = (int)((((i64)n_st + 3) & ~(i64)3) <= avail ? (((i64)n_st + 3) & ~(i64)3) : (avail & ~(i64)3));
+    const i64 rp0 = r0 & ~(i64)3;
+    const i64 rp_need = r1 + 1 - rp0;  // entries rp0 .. r1
+    const bool rp_smem = rp_need <= TMA_RP_CAP;
+    const i64 rp_avail = rowptr_len - rp0;
+    const int rp_bulk = rp_smem ? (int)(((rp_need + 3) & ~(i64)3) <= rp_avail ? ((rp_need + 3) & ~(i64)3) : (rp_avail & ~(i64)3)) : 0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint64_t pol = l2_evict_first_policy();
+        mbar_expect_tx(bar, (uint32_t)n_bulk * (uint32_t)(sizeof(Ti) + sizeof(T)) + (uint32_t)rp_bulk * (uint32_t)sizeof(Ti));
+        if (n_bulk > 0) {
+            bulk_g2s(scol, a.colval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(Ti), bar, pol);
+            bulk_g2s(sval, a.nzval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(T), bar, pol);
+        }
+        if (rp_bulk > 0) bulk_g2s(srp, a.rowptr + rp0, (uint32_t)rp_bulk * (uint32_t)sizeof(Ti), bar, pol);
+    }
+    // tails: the <= 3 elements a 16-byte copy would read past the end of an array (last tile of the matrix only)
+    for (int k = n_bulk + tid; k < n_st; k += THREADS) {
+        scol[k] = a.colval[s4 + k];
+        sval[k] = a.nzval[s4 + k];
+    }
+    if (rp_smem)
+        for (int k = rp_bulk + tid; k < (int)rp_need; k += THREADS) srp[k] = a.rowptr[rp0 + k];
+    mbar_wait(bar, 0);
+    __syncthreads();
+
+    const Ti* rp = rp_smem ? srp : a.rowptr;
+    const i64 rp_off = rp_smem ? rp0 : 0;
+    const i64 r_st = overrun ? r1 - 1 : r1;  // rows [r0, r_st) are completely staged
+    const i64 nrows_st = r_st - r0;
+
+    // Mode A needs about one short row per lane and a banded pattern (next row = same length, columns shifted by one)
+    bool mode_a = false;
+    if (!overrun && nrows_st >= THREADS / 2) {
+        int ok = 0;
+        if (tid < nrows_st - 1) {
+            const i64 r = r0 + tid;
+            const i64 b0 = (i64)rp[r - rp_off], b1 = (i64)rp[r - rp_off + 1], b2 = (i64)rp[r - rp_off + 2];
+            ok = (b1 - b0 == b2 - b1) && (b1 > b0) && (scol[b0 - 1 - s4] + 1 == scol[b1 - 1 - s4]);
+        }
+        const int cnt = __syncthreads_count(ok);
+        const int checked = (int)(nrows_st < THREADS ? nrows_st : THREADS) - 1;
+        mode_a = 4 * cnt >= 3 * checked;
+    }
+    if (mode_a) {
+        rows_walk<T, Ti, THREADS, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid);
+        return;
+    }
+    // Mode B, step 1 — products in place: consecutive lanes take consecutive nonzeros (4 each), all gathers of a lane
+    // are independent, so irregular columns get the most memory-level parallelism
+    for (int i = tid * 4; i < n_st; i += THREADS * 4) {
+        Ti c[4];
+        T v[4], xg[4];
+        ld4_shared(scol + i, c);
+        ld4_shared(sval + i, v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xg[k] = x_at<GHOST, T, Ti>(a.xv, (i + k < n_st) ? c[k] : (Ti)a.safe_col);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = el_mul(v[k], xg[k]);
+        st4_shared(sval + i, v);
+    }
+    __syncthreads();
+    if (nrows_st > 0) {
+        const i64 e_st = overrun ? (i64)rp[r_st - rp_off] - 1 : e;
+        const i64 avg = (e_st - s) / nrows_st;
+        if (avg <= 12) rows_sum<T, Ti, THREADS, 1>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
+        else if (avg <= 24) rows_sum<T, Ti, THREADS, 2>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
+        else if (avg <= 48) rows_sum<T, Ti, THREADS, 4>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
+        else if (avg <= 96) rows_sum<T, Ti, THREADS, 8>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
+        else if (avg <= 192) rows_sum<T, Ti, THREADS, 16>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
+        else rows_sum<T, Ti, THREADS, 32>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
+    }
+    if (overrun) {
+        // the last row: staged products first, the rest straight from global memory (coalesced, streaming)
+        const i64 r = r1 - 1;
+        const i64 b = (i64)rp[r - rp_off] - 1;  // absolute 0-based start
+        if (e - b <= a.long_threshold) {
+            T acc0 = el_zero(T()), acc1 = el_zero(T());
+            for (i64 k = b - s4 + tid; k < (i64)n_st; k += THREADS) acc0 = el_add(acc0, sval[k]);
+            i64 k = s4 + n_st + tid;
+            for (; k + THREADS < e; k += 2 * THREADS) {
+                const Ti c0 = ld_stream(a.colval + k), c1 = ld_stream(a.colval + k + THREADS);
+                const T v0 = ld_stream(a.nzval + k), v1 = ld_stream(a.nzval + k + THREADS);
+                acc0 = el_add(acc0, el_mul(v0, x_at<GHOST, T, Ti>(a.xv, c0)));
+                acc1 = el_add(acc1, el_mul(v1, x_at<GHOST, T, Ti>(a.xv, c1)));
+            }
+            if (k < e) acc0 = el_add(acc0, el_mul(ld_stream(a.nzval + k), x_at<GHOST, T, Ti>(a.xv, ld_stream(a.colval + k))));
+            const T tot = block_sum(el_add(acc0, acc1), red);
+            if (tid == 0) st_y(a.y + r, tot);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// very long rows ("merge-path split"): the row's nonzero range is cut into equal chunks, one CTA per chunk writes
+// one partial sum, a second kernel adds the partials of a row in chunk order.  Deterministic, no atomics.
+// ------------------------------------------------------------------------------------------------------------------
 template <class T, class Ti, bool GHOST>
 __global__ void __launch_bounds__(256) long_rows_partial_kernel(const Ti* __restrict__ rowptr, const Ti* __restrict__ colval,
                                                                 const T* __restrict__ nzval, const i64* __restrict__ long_rows,
@@ -669,7 +737,7 @@ static TileShape shape_of() {
     s.chunk = TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4;
     s.variant = spmv_variant();
     s.window = s.chunk - 64;
-    s.smem_elems = s.chunk + (s.variant == 1 ? 512 : 256);
+    s.smem_elems = s.chunk + (s.variant == 1 ? 512 : TMA_SLACK);
     return s;
 }
 TileShape tile_shape(int dtype) {
@@ -742,7 +810,7 @@ static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
         else spmv_tile_kernel<T, Ti, THREADS, GROUPS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
         return cudaGetLastError();
     }
-    const size_t smem = 16 + sizeof(Ti) * TMA_RP_CAP + (size_t)sh.smem_elems * (sizeof(Ti) + sizeof(T));
+    const size_t smem = tma_smem_bytes<T, Ti>();
     static bool configured[2][64] = {};  // per instantiation, per device: function attributes are per device
     int dev = 0;
     cudaGetDevice(&dev);
