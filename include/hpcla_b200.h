@@ -123,8 +123,9 @@ void hpcla_tb_destroy(hpcla_tb* tb);
  * writes to A.nzval — src/indexing.jl:932-982 — are seen by the next multiply). */
 int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nrows_local, int64_t ncols_compressed, int64_t nnz,
                      const void* d_rowptr, const void* d_colval, const void* d_nzval, hpcla_csr** out);
-/* query: number of row tiles, rows longer than the split threshold */
-int hpcla_csr_info(const hpcla_csr* csr, int64_t* ntiles_out, int64_t* nlong_rows_out);
+/* query: number of row tiles, rows longer than the split threshold, kernel variant picked from the structure
+ * (2 = TMA-staged row walk for banded/stencil-like matrices, 1 = vector loads + staged products otherwise) */
+int hpcla_csr_info(const hpcla_csr* csr, int64_t* ntiles_out, int64_t* nlong_rows_out, int* variant_out);
 void hpcla_csr_destroy(hpcla_csr* csr);
 
 /* Binds (A, VectorPlan) to device buffers: the device copy of send indices, the packed send buffer, `gathered`

@@ -70,7 +70,7 @@ SIGNATURES = {
     "hpcla_tb_result": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hpcla_tb_destroy": (None, [_vp]),
     "hpcla_csr_create": (_i, [_vp, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
-    "hpcla_csr_info": (_i, [_vp, _vp, _vp]),
+    "hpcla_csr_info": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_csr_destroy": (None, [_vp]),
     "hpcla_spmv_create": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hpcla_spmv_run": (_i, [_vp, _vp, _vp, _vp]),

@@ -285,7 +285,26 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     A->d_rowptr = d_rowptr;
     A->d_colval = d_colval;
     A->d_nzval = d_nzval;
-    A->shape = tile_shape(dtype);
+    cudaStream_t st = ctx->halo_stream;
+    // Kernel variant: 2 (TMA-staged operands, row walk) for banded / stencil-like structure, 1 (vector loads + staged
+    // products, most memory-level parallelism for scattered columns) otherwise.  HPCLA_SPMV_VARIANT=1|2 overrides.
+    int variant = 0;
+    if (const char* e = getenv("HPCLA_SPMV_VARIANT")) variant = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
+    if (variant == 0) {
+        variant = 2;
+        if (nrows >= 2 && nnz > 0) {
+            unsigned long long* d_cnt = nullptr;
+            unsigned long long cnt = 0;
+            CU_TRY(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+            CU_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
+            CU_TRY(launch_banded_stat(itype, d_rowptr, d_colval, nrows, d_cnt, st));
+            CU_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(d_cnt);
+            if (2 * (i64)cnt < nrows - 1) variant = 1;
+        }
+    }
+    A->shape = tile_shape(dtype, variant);
     if (A->shape.variant == 2 && nrows > 0) {
         // short rows: one lane per row, so size the window to about one row per thread (one pass over the rows)
         const double avg = (double)nnz / (double)nrows;
@@ -305,7 +324,6 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     }
     A->long_threshold = 16384;
     A->chunk_nnz = 16384;
-    cudaStream_t st = ctx->halo_stream;
     CU_TRY(cudaMalloc(&A->d_tiles, sizeof(TileDesc) * (size_t)(A->ntiles + 1)));
     CU_TRY(launch_build_tiles(itype, d_rowptr, nrows, nnz, A->shape.window, A->d_tiles, A->ntiles, st));
     // rows longer than the split threshold (rare: power-law tails)
@@ -347,10 +365,11 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     return HPCLA_OK;
 }
 
-extern "C" int hpcla_csr_info(const hpcla_csr* A, int64_t* ntiles_out, int64_t* nlong_out) {
+extern "C" int hpcla_csr_info(const hpcla_csr* A, int64_t* ntiles_out, int64_t* nlong_out, int* variant_out) {
     if (!A) return fail(HPCLA_ERR_ARG, "hpcla_csr_info: null");
     if (ntiles_out) *ntiles_out = A->ntiles;
     if (nlong_out) *nlong_out = A->nlong;
+    if (variant_out) *variant_out = A->shape.variant;
     return HPCLA_OK;
 }
 

@@ -21,7 +21,7 @@ struct TileShape {
     int smem_elems;  // staged nonzeros that fit in shared memory = chunk + slack
     int variant;     // 1 = LDG + staged products, 2 = TMA-staged operands
 };
-TileShape tile_shape(int dtype);
+TileShape tile_shape(int dtype, int variant);
 
 struct SpmvLaunch {
     int dtype, itype;
@@ -46,6 +46,8 @@ struct SpmvLaunch {
 
 cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles,
                                cudaStream_t st);
+// *count_out (device, pre-zeroed) += rows whose successor has the same length and first column + 1
+cudaError_t launch_banded_stat(int itype, const void* rowptr, const void* colval, i64 nrows, unsigned long long* count_out, cudaStream_t st);
 // rows longer than threshold: writes their local row ids (ascending not guaranteed) into rows_out (capacity cap), count via *count_out (device)
 cudaError_t launch_find_long_rows(int itype, const void* rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
                                   unsigned long long* count_out, cudaStream_t st);

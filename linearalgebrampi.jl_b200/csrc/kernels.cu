@@ -315,25 +315,36 @@ __device__ __forceinline__ T block_sum(T v, T* sh /* [32] */) {
     return r;  // valid in warp 0
 }
 
-// Mode A — row walk: G = 1 lane per row, operands read from shared memory, x gathered per row entry.  Consecutive lanes
-// own consecutive rows: on banded matrices a warp's gathers are coalesced; the sum runs left to right (reference order).
-template <class T, class Ti, int THREADS, bool GHOST>
+// Mode A — row walk: G lanes per row (interleaved: lane g takes entries g, g+G, ...), operands read from shared
+// memory, x gathered per entry.  Lanes of a warp own consecutive rows, so on banded matrices the gathers of one warp
+// instruction fall into a few contiguous runs (coalesced).  G = 1 sums left to right: the reference's order, bit for bit.
+template <class T, class Ti, int THREADS, int G, bool GHOST>
 __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const Ti* rp, i64 rp_off, const XView<T>& xv, T* __restrict__ y, i64 r0,
                                           i64 r1, i64 s4, int tid) {
-    for (i64 r = r0 + tid; r < r1; r += THREADS) {
-        const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
-        const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
+    constexpr int RPP = THREADS / G;
+    const int lane = tid % G;
+    for (i64 base = r0; base < r1; base += RPP) {
+        const i64 r = base + tid / G;
+        const bool valid = r < r1;
         T acc = el_zero(T());
-        int k = b;
-        for (; k + 4 <= e; k += 4) {  // independent loads first (4 at a time), then the adds in the reference's order
-            T p[4];
+        if (valid) {
+            const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
+            const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
+            int k = b + lane;
+            for (; k + 3 * G < e; k += 4 * G) {  // 4 independent gathers in flight per lane, then the adds in order
+                T p[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) p[u] = el_mul(sval[k + u], x_at<GHOST, T, Ti>(xv, scol[k + u]));
+                for (int u = 0; u < 4; ++u) p[u] = el_mul(sval[k + u * G], x_at<GHOST, T, Ti>(xv, scol[k + u * G]));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
+                for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
+            }
+            for (; k < e; k += G) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
         }
-        for (; k < e; ++k) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
-        st_y(y + r, acc);
+        if (G > 1) {
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+        }
+        if (valid && lane == 0) st_y(y + r, acc);
     }
 }
 
@@ -440,9 +451,9 @@ __global__ void __launch_bounds__(THREADS, tma_min_ctas<T, Ti, GHOST>()) spmv_ti
     const i64 r_st = overrun ? r1 - 1 : r1;  // rows [r0, r_st) are completely staged
     const i64 nrows_st = r_st - r0;
 
-    // Mode A needs about one short row per lane and a banded pattern (next row = same length, columns shifted by one)
+    // Mode A needs a banded pattern (next row: same length, columns shifted by one); lanes per row fill the CTA
     bool mode_a = false;
-    if (!overrun && nrows_st >= THREADS / 2) {
+    if (!overrun && nrows_st >= 8) {
         int ok = 0;
         if (tid < nrows_st - 1) {
             const i64 r = r0 + tid;
@@ -454,7 +465,14 @@ __global__ void __launch_bounds__(THREADS, tma_min_ctas<T, Ti, GHOST>()) spmv_ti
         mode_a = 4 * cnt >= 3 * checked;
     }
     if (mode_a) {
-        rows_walk<T, Ti, THREADS, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid);
+        int G = 1;
+        while (G < 8 && nrows_st * (2 * G) <= THREADS) G *= 2;
+        switch (G) {
+            case 1: rows_walk<T, Ti, THREADS, 1, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
+            case 2: rows_walk<T, Ti, THREADS, 2, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
+            case 4: rows_walk<T, Ti, THREADS, 4, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
+            default: rows_walk<T, Ti, THREADS, 8, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
+        }
         return;
     }
     // Mode B, step 1 — products in place: consecutive lanes take consecutive nonzeros (4 each), all gathers of a lane
@@ -567,6 +585,19 @@ __global__ void build_tiles_kernel(const Ti* __restrict__ rowptr, i64 nrows, int
     }
     tiles[k].row = r;
     tiles[k].nnz = (i64)rowptr[r] - 1;
+}
+
+// rows whose successor has the same length and its first column shifted by one ("banded"): picks the kernel variant
+template <class Ti>
+__global__ void __launch_bounds__(256) banded_stat_kernel(const Ti* __restrict__ rowptr, const Ti* __restrict__ colval, i64 nrows, unsigned long long* count) {
+    const i64 r = (i64)blockIdx.x * 256 + threadIdx.x;
+    int ok = 0;
+    if (r + 1 < nrows) {
+        const i64 b0 = (i64)rowptr[r], b1 = (i64)rowptr[r + 1], b2 = (i64)rowptr[r + 2];
+        ok = (b1 - b0 == b2 - b1) && (b1 > b0) && (colval[b0 - 1] + 1 == colval[b1 - 1]);
+    }
+    const int cnt = __syncthreads_count(ok);
+    if (threadIdx.x == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
 }
 
 template <class Ti>
@@ -729,21 +760,20 @@ __global__ void cg_update_p_kernel(i64 n, const T* __restrict__ r, T* __restrict
 // host-side launchers
 // ==================================================================================================================
 
-int spmv_variant();
 template <class T>
-static TileShape shape_of() {
+static TileShape shape_of(int variant) {
     TileShape s;
     s.threads = TileCfg<T>::THREADS;
     s.chunk = TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4;
-    s.variant = spmv_variant();
+    s.variant = variant;
     s.window = s.chunk - 64;
     s.smem_elems = s.chunk + (s.variant == 1 ? 512 : TMA_SLACK);
     return s;
 }
-TileShape tile_shape(int dtype) {
-    if (dtype == HPCLA_F32) return shape_of<float>();
-    if (dtype == HPCLA_F64) return shape_of<double>();
-    return shape_of<cplx>();
+TileShape tile_shape(int dtype, int variant) {
+    if (dtype == HPCLA_F32) return shape_of<float>(variant);
+    if (dtype == HPCLA_F64) return shape_of<double>(variant);
+    return shape_of<cplx>(variant);
 }
 
 static inline int blocks_for(i64 n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -753,6 +783,14 @@ cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz
     const int blocks = blocks_for(ntiles + 1, 256);
     if (itype == HPCLA_I32) build_tiles_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, nrows, window, tiles, ntiles);
     else build_tiles_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, nrows, window, tiles, ntiles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_banded_stat(int itype, const void* rowptr, const void* colval, i64 nrows, unsigned long long* count_out, cudaStream_t st) {
+    if (nrows < 2) return cudaSuccess;
+    const int blocks = blocks_for(nrows, 256);
+    if (itype == HPCLA_I32) banded_stat_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, (const int*)colval, nrows, count_out);
+    else banded_stat_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, (const long long*)colval, nrows, count_out);
     return cudaGetLastError();
 }
 
@@ -783,10 +821,6 @@ static XView<T> make_xview(const void* x_own, const void* gathered, i64 own_lo, 
     return v;
 }
 
-int spmv_variant() {
-    const char* e = getenv("HPCLA_SPMV_VARIANT");
-    return (e && e[0] == '1') ? 1 : 2;  // 1 = LDG + staged products, 2 = TMA-staged operands (default)
-}
 
 template <class T, class Ti>
 static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {

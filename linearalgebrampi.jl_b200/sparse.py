@@ -344,9 +344,9 @@ def spmv_info(A: HPCSparseMatrix, x: HPCVector) -> Dict[str, int]:
     ni, nb = ctypes.c_int64(), ctypes.c_int64()
     xin, sc = ctypes.c_int(), ctypes.c_int()
     _lib.check(L.hpcla_spmv_info(op, ctypes.byref(ni), ctypes.byref(nb), ctypes.byref(xin), ctypes.byref(sc)))
-    nt, nl = ctypes.c_int64(), ctypes.c_int64()
-    _lib.check(L.hpcla_csr_info(_csr_handle(A), ctypes.byref(nt), ctypes.byref(nl)))
-    return {"tiles": nt.value, "long_rows": nl.value, "interior_tiles": ni.value, "boundary_tiles": nb.value,
+    nt, nl, var = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+    _lib.check(L.hpcla_csr_info(_csr_handle(A), ctypes.byref(nt), ctypes.byref(nl), ctypes.byref(var)))
+    return {"tiles": nt.value, "long_rows": nl.value, "kernel_variant": var.value, "interior_tiles": ni.value, "boundary_tiles": nb.value,
             "x_in_place": xin.value, "sends_contiguous": sc.value, "launches": int(L.hpcla_spmv_launch_count(op))}
 
 

@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--reps", type=int, default=100)
     ap.add_argument("--windows", default="")
+    ap.add_argument("--variants", default="1,2")
+    ap.add_argument("--n", type=int, default=20_000_000, help="rows of the power-law matrix")
     args = ap.parse_args()
     S = la.synth
     if args.workload == "poisson256":
@@ -71,7 +73,7 @@ def main():
     elif args.workload == "powerlaw":
         T, Ti, tn, tin = np.float32, np.int32, "f32", "i32"
         b = la.backend_cuda_serial(T, Ti)
-        A = S.powerlaw_matrix(20_000_000, b)
+        A = S.powerlaw_matrix(args.n, b)
     else:
         raise SystemExit("unknown workload")
     n = A.shape[0]
@@ -79,7 +81,7 @@ def main():
     y = la.HPCVector.zeros(b, n)
     bts, fl = algorithmic_bytes_flops(n, n, A.nnz_local, tn, tin, "mul")
     print(f"workload {args.workload}: n={n} nnz={A.nnz_local} bytes={bts/1e9:.3f} GB")
-    configs = [{"HPCLA_SPMV_VARIANT": 1}, {"HPCLA_SPMV_VARIANT": 2}]
+    configs = [{}] + [{"HPCLA_SPMV_VARIANT": int(v)} for v in args.variants.split(",") if v]
     for w in [int(v) for v in args.windows.split(",") if v]:
         configs.append({"HPCLA_SPMV_VARIANT": 2, "HPCLA_TILE_WINDOW": w})
     ref = None
@@ -88,7 +90,7 @@ def main():
         if ref is None:
             ref = res
         err = float((res - ref).abs().max() / ref.abs().max())
-        print(f"{str(env):60s} {ms*1e3:9.1f} us  {bts/ms/1e6:8.1f} GB/s  {fl/ms/1e6:8.1f} GFLOP/s  tiles={info['tiles']} maxrelerr_vs_first={err:.2e}", flush=True)
+        print(f"{str(env):60s} {ms*1e3:9.1f} us  {bts/ms/1e6:8.1f} GB/s  {fl/ms/1e6:8.1f} GFLOP/s  tiles={info['tiles']} variant={info['kernel_variant']} maxrelerr_vs_first={err:.2e}", flush=True)
 
 
 if __name__ == "__main__":
