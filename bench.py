@@ -374,7 +374,7 @@ def run_b200_arm(args, spec):
     per_gpu_gbs = gbs / world
     roofline = {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu_gbs / NOMINAL_HBM_GBS,
-                "kernel": ("spmv_tile_tma_kernel" if info["kernel_variant"] == 2 else "spmv_tile_kernel") + ("" if world == 1 else " (interior + boundary launches; step time includes the NCCL halo)"),
+                "kernel": ("spmv_rowwalk_kernel" if info["rowwalk_tiles"] >= info["general_tiles"] else "spmv_tile_kernel") + ("" if world == 1 else " (interior + boundary launches; step time includes the NCCL halo)"),
                 "algorithmic_bytes_per_step": bytes_step, "flops_per_step": flops_step}
 
     cpu = None
@@ -389,7 +389,7 @@ def run_b200_arm(args, spec):
             "data": "synthetic",
             "config": {"workload": spec["name"], "index_type": spec["Ti"], "op": op, "rows": n, "nnz": nnz, "l2": "inputs exceed L2 (no flush needed)" if bytes_step / world > 2 * 126e6 else "inputs do NOT exceed L2",
                        "tiles": info["tiles"], "interior_tiles": info["interior_tiles"], "boundary_tiles": info["boundary_tiles"],
-                       "x_in_place": info["x_in_place"], "kernel_variant": info["kernel_variant"], "check": check, "setup_s": round(setup_s, 2)},
+                       "x_in_place": info["x_in_place"], "lanes_per_row": info["lanes_per_row"], "tile_window": info["tile_window"], "rowwalk_tiles": info["rowwalk_tiles"], "general_tiles": info["general_tiles"], "check": check, "setup_s": round(setup_s, 2)},
             "achieved_gbs": gbs, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(region),
         }

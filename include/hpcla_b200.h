@@ -123,9 +123,13 @@ void hpcla_tb_destroy(hpcla_tb* tb);
  * writes to A.nzval — src/indexing.jl:932-982 — are seen by the next multiply). */
 int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nrows_local, int64_t ncols_compressed, int64_t nnz,
                      const void* d_rowptr, const void* d_colval, const void* d_nzval, hpcla_csr** out);
-/* query: number of row tiles, rows longer than the split threshold, kernel variant picked from the structure
- * (2 = TMA-staged row walk for banded/stencil-like matrices, 1 = vector loads + staged products otherwise) */
-int hpcla_csr_info(const hpcla_csr* csr, int64_t* ntiles_out, int64_t* nlong_rows_out, int* variant_out);
+/* query: number of row tiles, rows longer than the split threshold, and the lanes per row of the row-walk kernel
+ * picked from the mean row length (1, 2, 4, ... 32; 0 = the matrix is irregular and uses the general kernel only) */
+int hpcla_csr_info(const hpcla_csr* csr, int64_t* ntiles_out, int64_t* nlong_rows_out, int* lanes_out);
+/* query: tiles taken by the TMA-staged row-walk kernel / by the general kernel / holding no row, and the tile window
+ * (stored entries per tile) */
+int hpcla_csr_tile_classes(const hpcla_csr* csr, int64_t* n_rowwalk_out, int64_t* n_general_out, int64_t* n_empty_out,
+                           int* window_out);
 void hpcla_csr_destroy(hpcla_csr* csr);
 
 /* Binds (A, VectorPlan) to device buffers: the device copy of send indices, the packed send buffer, `gathered`

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhpcla_b200.so")
+# HPCLA_LIB: another build of the same library (kernel A/B experiments of tools/tune_spmv.py); never a fallback
+LIB_PATH = os.environ.get("HPCLA_LIB") or os.path.join(_HERE, "libhpcla_b200.so")
 
 F32, F64, C128 = 0, 1, 2
 I32, I64 = 0, 1
@@ -71,6 +72,7 @@ SIGNATURES = {
     "hpcla_tb_destroy": (None, [_vp]),
     "hpcla_csr_create": (_i, [_vp, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "hpcla_csr_info": (_i, [_vp, _vp, _vp, _vp]),
+    "hpcla_csr_tile_classes": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hpcla_csr_destroy": (None, [_vp]),
     "hpcla_spmv_create": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hpcla_spmv_run": (_i, [_vp, _vp, _vp, _vp]),

@@ -34,32 +34,36 @@ def needs_build() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """defines / out: an alternate build of the same library with -D knobs (kernel A/B experiments; loaded through
+    HPCLA_LIB by tools/tune_spmv.py)."""
+    if not force and not defines and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" if not defines else "build_" + "_".join(d.replace("=", "") for d in defines))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for s in SOURCES:
         o = os.path.join(objdir, os.path.splitext(s)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {s}:\n{out}")
+            raise RuntimeError(f"nvcc failed on {s}:\n{log}")
         if verbose:
-            print(out)
+            print(log)
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "--cudart", "static", "-Xcompiler", "-fPIC",
-            "-Xlinker", "--no-undefined", "-o", LIB, *objs, "-ldl", "-lpthread"]
+            "-Xlinker", "--no-undefined", "-o", out, *objs, "-ldl", "-lpthread"]
     subprocess.check_call(link)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=os.path.join(HERE, outs[0]) if outs else LIB))

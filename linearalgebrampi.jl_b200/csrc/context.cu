@@ -107,6 +107,8 @@ struct hpcla_csr {
     TileShape shape{};
     TileDesc* d_tiles = nullptr;
     i64 ntiles = 0;
+    std::vector<unsigned char> tile_class;  // per tile: 0 no rows, 1 row-walk kernel, 2 general kernel
+    i64 n_class[3] = {0, 0, 0};
     i64 long_threshold = 0, chunk_nnz = 0;
     i64 nlong = 0, nchunks = 0;
     i64 *d_long_rows = nullptr, *d_chunk_ptr = nullptr;
@@ -139,8 +141,8 @@ struct hpcla_spmv {
     void* d_sendbuf = nullptr;
     i64* d_send_idx = nullptr;                              // concatenated send_indices (all peers)
     i64 *d_local_src = nullptr, *d_local_dst = nullptr;     // only when needed (fallback / gather hook)
-    int *d_list_int = nullptr, *d_list_bnd = nullptr;
-    int n_int = 0, n_bnd = 0;
+    int* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
+    int n_list[2][2] = {{0, 0}, {0, 0}};
     cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
     bool halo_recorded = false;
     // in-flight call
@@ -148,6 +150,8 @@ struct hpcla_spmv {
     void* cur_y = nullptr;
     cudaStream_t cur_stream = nullptr;
     int phase = 0;  // 0 idle, 1 multiply begun, 2 gather begun
+    const void* persist_x = nullptr;  // x.v currently covered by the L2 persisting window (HPCLA_X_PERSIST)
+    cudaStream_t persist_stream = nullptr;
     std::atomic<long long> epoch{0};  // exchanges begun (a peer's finish checks that I have begun the matching one)
     i64 launches = 0;
 };
@@ -286,46 +290,39 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     A->d_colval = d_colval;
     A->d_nzval = d_nzval;
     cudaStream_t st = ctx->halo_stream;
-    // Kernel variant: 2 (TMA-staged operands, row walk) for banded / stencil-like structure, 1 (vector loads + staged
-    // products, most memory-level parallelism for scattered columns) otherwise.  HPCLA_SPMV_VARIANT=1|2 overrides.
-    int variant = 0;
-    if (const char* e = getenv("HPCLA_SPMV_VARIANT")) variant = (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : 0;
-    if (variant == 0) {
-        variant = 2;
-        if (nrows >= 2 && nnz > 0) {
-            unsigned long long* d_cnt = nullptr;
-            unsigned long long cnt = 0;
-            CU_TRY(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
-            CU_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), st));
-            CU_TRY(launch_banded_stat(itype, d_rowptr, d_colval, nrows, d_cnt, st));
-            CU_TRY(cudaMemcpyAsync(&cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
-            cudaFree(d_cnt);
-            if (2 * (i64)cnt < nrows - 1) variant = 1;
-        }
-    }
-    A->shape = tile_shape(dtype, variant);
-    if (A->shape.variant == 2 && nrows > 0) {
-        // short rows: one lane per row, so size the window to about one row per thread (one pass over the rows)
-        const double avg = (double)nnz / (double)nrows;
-        if (avg > 0 && avg <= 16.0) {
-            int w = ((int)(A->shape.threads * avg)) & ~3;
-            if (w >= 256 && w < A->shape.window) A->shape.window = w;
-        }
-    }
-    if (const char* e = getenv("HPCLA_TILE_WINDOW")) {
-        int w = atoi(e) & ~3;
-        if (w >= 64 && w <= A->shape.smem_elems - 8) A->shape.window = w;
-    }
-    A->ntiles = nnz / A->shape.window + 1;
-    if (A->ntiles >= (i64)INT32_MAX) {
-        delete A;
-        return fail(HPCLA_ERR_ARG, "hpcla_csr_create: too many tiles");
-    }
+    // Tile shape from the mean row length, then the kernel class of every tile (row walk for balanced, fully staged
+    // tiles; general otherwise).  A matrix whose tiles are mostly general is re-tiled with the general kernel's own
+    // shape.  Tuning hooks: HPCLA_LANES, HPCLA_TILE_WINDOW, HPCLA_SPMV_KIND=general|rowwalk.
+    int lanes_override = 0, window_override = 0, kind = 0;
+    if (const char* e = getenv("HPCLA_LANES")) lanes_override = atoi(e);
+    if (const char* e = getenv("HPCLA_TILE_WINDOW")) window_override = atoi(e);
+    if (const char* e = getenv("HPCLA_SPMV_KIND")) kind = (e[0] == 'g') ? 2 : (e[0] == 'r') ? 1 : 0;
+    const double avg_row = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
     A->long_threshold = 16384;
     A->chunk_nnz = 16384;
-    CU_TRY(cudaMalloc(&A->d_tiles, sizeof(TileDesc) * (size_t)(A->ntiles + 1)));
-    CU_TRY(launch_build_tiles(itype, d_rowptr, nrows, nnz, A->shape.window, A->d_tiles, A->ntiles, st));
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool irregular = (pass == 1) || kind == 2;
+        A->shape = tile_shape(dtype, itype, avg_row, irregular, lanes_override, window_override);
+        A->ntiles = nnz / A->shape.window + 1;
+        if (A->ntiles >= (i64)INT32_MAX) {
+            delete A;
+            return fail(HPCLA_ERR_ARG, "hpcla_csr_create: too many tiles");
+        }
+        if (A->d_tiles) cudaFree(A->d_tiles);
+        A->d_tiles = nullptr;
+        CU_TRY(cudaMalloc(&A->d_tiles, sizeof(TileDesc) * (size_t)(A->ntiles + 1)));
+        CU_TRY(launch_build_tiles(itype, d_rowptr, nrows, nnz, A->shape.window, A->d_tiles, A->ntiles, st));
+        unsigned char* d_cls = nullptr;
+        CU_TRY(cudaMalloc(&d_cls, (size_t)A->ntiles));
+        CU_TRY(launch_tile_class(itype, d_rowptr, A->d_tiles, A->ntiles, A->shape.cap, A->shape.rp_cap, d_cls, st));
+        A->tile_class.assign((size_t)A->ntiles, 0);
+        CU_TRY(cudaMemcpyAsync(A->tile_class.data(), d_cls, (size_t)A->ntiles, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_cls);
+        A->n_class[0] = A->n_class[1] = A->n_class[2] = 0;
+        for (unsigned char c : A->tile_class) A->n_class[c] += 1;
+        if (irregular || kind == 1 || A->n_class[1] >= A->n_class[2]) break;
+    }
     // rows longer than the split threshold (rare: power-law tails)
     const i64 cap = nnz / A->long_threshold + 1;
     unsigned long long* d_count = nullptr;
@@ -369,7 +366,16 @@ extern "C" int hpcla_csr_info(const hpcla_csr* A, int64_t* ntiles_out, int64_t* 
     if (!A) return fail(HPCLA_ERR_ARG, "hpcla_csr_info: null");
     if (ntiles_out) *ntiles_out = A->ntiles;
     if (nlong_out) *nlong_out = A->nlong;
-    if (variant_out) *variant_out = A->shape.variant;
+    if (variant_out) *variant_out = A->shape.lanes;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_csr_tile_classes(const hpcla_csr* A, int64_t* n_rowwalk, int64_t* n_general, int64_t* n_empty, int* window_out) {
+    if (!A) return fail(HPCLA_ERR_ARG, "hpcla_csr_tile_classes: null");
+    if (n_rowwalk) *n_rowwalk = A->n_class[1];
+    if (n_general) *n_general = A->n_class[2];
+    if (n_empty) *n_empty = A->n_class[0];
+    if (window_out) *window_out = A->shape.window;
     return HPCLA_OK;
 }
 
@@ -459,30 +465,29 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
     CU_TRY(cudaEventCreateWithFlags(&op->ev_x, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&op->ev_packed, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
-    // interior / boundary tile lists: a tile is boundary iff one of its stored columns is a ghost
-    if (op->has_ghost && A->ntiles > 0) {
-        unsigned char* d_flags = nullptr;
-        CU_TRY(cudaMalloc(&d_flags, (size_t)A->ntiles));
-        CU_TRY(launch_classify_tiles(A->itype, A->d_colval, A->d_tiles, A->ntiles, op->own_lo, op->own_n, d_flags, ctx->halo_stream));
-        std::vector<unsigned char> flags((size_t)A->ntiles);
-        CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, flags.size(), cudaMemcpyDeviceToHost, ctx->halo_stream));
-        CU_TRY(cudaStreamSynchronize(ctx->halo_stream));
-        cudaFree(d_flags);
-        std::vector<int> li, lb;
-        for (i64 t = 0; t < A->ntiles; ++t) (flags[(size_t)t] ? lb : li).push_back((int)t);
-        op->n_int = (int)li.size();
-        op->n_bnd = (int)lb.size();
-        if (op->n_int) {
-            CU_TRY(cudaMalloc(&op->d_list_int, sizeof(int) * li.size()));
-            CU_TRY(cudaMemcpy(op->d_list_int, li.data(), sizeof(int) * li.size(), cudaMemcpyHostToDevice));
+    // tile lists per kernel class, interior / boundary: a tile is boundary iff one of its stored columns is a ghost
+    {
+        std::vector<unsigned char> flags((size_t)A->ntiles, 0);
+        if (op->has_ghost && A->ntiles > 0) {
+            unsigned char* d_flags = nullptr;
+            CU_TRY(cudaMalloc(&d_flags, (size_t)A->ntiles));
+            CU_TRY(launch_classify_tiles(A->itype, A->d_colval, A->d_tiles, A->ntiles, op->own_lo, op->own_n, d_flags, ctx->halo_stream));
+            CU_TRY(cudaMemcpyAsync(flags.data(), d_flags, flags.size(), cudaMemcpyDeviceToHost, ctx->halo_stream));
+            CU_TRY(cudaStreamSynchronize(ctx->halo_stream));
+            cudaFree(d_flags);
         }
-        if (op->n_bnd) {
-            CU_TRY(cudaMalloc(&op->d_list_bnd, sizeof(int) * lb.size()));
-            CU_TRY(cudaMemcpy(op->d_list_bnd, lb.data(), sizeof(int) * lb.size(), cudaMemcpyHostToDevice));
+        std::vector<int> lists[2][2];
+        for (i64 t = 0; t < A->ntiles; ++t) {
+            const int c = A->tile_class[(size_t)t];
+            if (c) lists[c - 1][flags[(size_t)t] ? 1 : 0].push_back((int)t);
         }
-    } else {
-        op->n_int = (int)A->ntiles;
-        op->n_bnd = 0;
+        for (int c = 0; c < 2; ++c)
+            for (int g = 0; g < 2; ++g) {
+                op->n_list[c][g] = (int)lists[c][g].size();
+                if (lists[c][g].empty() || (i64)lists[c][g].size() == A->ntiles) continue;  // all tiles, in order: no list
+                CU_TRY(cudaMalloc(&op->d_list[c][g], sizeof(int) * lists[c][g].size()));
+                CU_TRY(cudaMemcpy(op->d_list[c][g], lists[c][g].data(), sizeof(int) * lists[c][g].size(), cudaMemcpyHostToDevice));
+            }
     }
     op->seq = ctx->op_seq++;
     if (ctx->group) {
@@ -497,8 +502,8 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
 
 extern "C" int hpcla_spmv_info(const hpcla_spmv* op, int64_t* n_int, int64_t* n_bnd, int* x_in_place, int* sends_contiguous) {
     if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_info: null");
-    if (n_int) *n_int = op->n_int;
-    if (n_bnd) *n_bnd = op->n_bnd;
+    if (n_int) *n_int = op->n_list[0][0] + op->n_list[1][0];
+    if (n_bnd) *n_bnd = op->n_list[0][1] + op->n_list[1][1];
     if (x_in_place) *x_in_place = op->x_in_place ? 1 : 0;
     if (sends_contiguous) *sends_contiguous = op->sends_contiguous ? 1 : 0;
     return HPCLA_OK;
@@ -519,8 +524,8 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
     cudaFree(op->d_send_idx);
     cudaFree(op->d_local_src);
     cudaFree(op->d_local_dst);
-    cudaFree(op->d_list_int);
-    cudaFree(op->d_list_bnd);
+    for (int c = 0; c < 2; ++c)
+        for (int g = 0; g < 2; ++g) cudaFree(op->d_list[c][g]);
     if (op->ev_x) cudaEventDestroy(op->ev_x);
     if (op->ev_packed) cudaEventDestroy(op->ev_packed);
     if (op->ev_halo) cudaEventDestroy(op->ev_halo);
@@ -635,6 +640,19 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
     L.long_threshold = A->long_threshold;
 }
 
+// both kernel classes over the interior (which = 0) or boundary (which = 1) tiles
+static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t stream) {
+    for (int c = 0; c < 2; ++c) {
+        L.tile_list = op->d_list[c][which];
+        L.n_launch = op->n_list[c][which];
+        if (L.n_launch <= 0) continue;
+        if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
+        else CU_TRY(launch_spmv_general(L, stream));
+        op->launches += 1;
+    }
+    return HPCLA_OK;
+}
+
 static int launch_long(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stream) {
     const hpcla_csr* A = op->csr;
     if (A->nlong == 0) return HPCLA_OK;
@@ -661,6 +679,40 @@ static int launch_long(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stre
     return HPCLA_OK;
 }
 
+// Experiment hook, HPCLA_X_PERSIST=<percent>: mark x.v as an L2 persisting access window on the caller's stream (hit
+// ratio = percent / 100), so that scattered gathers of an x larger than the effective L2 keep a resident fraction.
+static void maybe_persist_x(hpcla_spmv* op, const void* d_x, cudaStream_t stream) {
+    static int pct = -1;
+    if (pct < 0) {
+        const char* e = getenv("HPCLA_X_PERSIST");
+        pct = e ? atoi(e) : 0;
+    }
+    if (pct <= 0 || !d_x || (op->persist_x == d_x && op->persist_stream == stream)) return;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, op->ctx->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, op->ctx->device);
+    if (max_persist <= 0 || max_window <= 0) return;
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+    cudaStreamAttrValue v;
+    std::memset(&v, 0, sizeof v);
+    const size_t bytes = (size_t)op->n_x_local * dtype_size(op->csr->dtype);
+    v.accessPolicyWindow.base_ptr = const_cast<void*>(d_x);
+    v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
+    v.accessPolicyWindow.hitRatio = pct >= 100 ? 1.0f : (float)pct / 100.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaError_t e = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+    static bool told = false;
+    if (!told) {
+        fprintf(stderr, "[hpcla] HPCLA_X_PERSIST=%d: max persisting L2 %d MiB, max window %d MiB, x %zu MiB: %s\n", pct, max_persist >> 20, max_window >> 20,
+                bytes >> 20, cudaGetErrorString(e));
+        told = true;
+    }
+    cudaGetLastError();
+    op->persist_x = d_x;
+    op->persist_stream = stream;
+}
+
 extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream_) {
     if (!op || (op->n_x_local > 0 && !d_x) || (op->csr->nrows > 0 && !d_y)) return fail(HPCLA_ERR_ARG, "hpcla_spmv_begin: null");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_begin: the previous call was not finished");
@@ -670,6 +722,7 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     op->cur_x = d_x;
     op->cur_y = d_y;
     op->cur_stream = stream;
+    maybe_persist_x(op, d_x, stream);
     if (op->has_peers) {
         rc = exchange_begin(op, d_x, stream);
         if (rc) return rc;
@@ -680,18 +733,11 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     }
     SpmvLaunch L;
     fill_launch(op, L, d_x, d_y);
-    if (op->has_ghost) {  // interior tiles: only own columns (so the ghost-free kernel), run while the halo is in flight
-        L.tile_list = op->d_list_int;
-        L.n_launch = op->n_int;
-        L.has_ghost = false;
-    } else {
-        L.tile_list = nullptr;
-        L.n_launch = (int)op->csr->ntiles;
-    }
-    if (L.n_launch > 0) {
-        CU_TRY(launch_spmv_tiles(L, stream));
-        op->launches += 1;
-    }
+    // interior tiles (all tiles when there are no ghosts) read own columns only: the ghost-free kernels, run while the
+    // halo is in flight
+    L.has_ghost = false;
+    rc = launch_tiles(op, L, 0, stream);
+    if (rc) return rc;
     if (!op->has_ghost) {
         rc = launch_long(op, L, stream);
         if (rc) return rc;
@@ -719,12 +765,8 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
     if (op->has_ghost) {
         SpmvLaunch L;
         fill_launch(op, L, op->cur_x, op->cur_y);
-        L.tile_list = op->d_list_bnd;
-        L.n_launch = op->n_bnd;
-        if (L.n_launch > 0) {
-            CU_TRY(launch_spmv_tiles(L, stream));
-            op->launches += 1;
-        }
+        rc = launch_tiles(op, L, 1, stream);
+        if (rc) return rc;
         rc = launch_long(op, L, stream);
         if (rc) return rc;
     }

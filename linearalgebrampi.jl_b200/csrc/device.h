@@ -13,15 +13,18 @@ struct TileDesc {
     i64 nnz;
 };
 
-// Tunables of the tile kernel for one element type (see kernels.cu).
+// Tile shape of one matrix (see kernels.cu: shape_of).
 struct TileShape {
-    int threads;     // CTA size
-    int chunk;       // nonzeros staged per round = threads * groups * 4
-    int window;      // nonzeros per tile window = chunk - 64
-    int smem_elems;  // staged nonzeros that fit in shared memory = chunk + slack
-    int variant;     // 1 = LDG + staged products, 2 = TMA-staged operands
+    int threads;        // CTA size of the row-walk kernel
+    int lanes;          // row walk: lanes per row (1, 2, 4, ..., 32); 0: the matrix uses the general kernel only
+    int window;         // nonzeros per tile window
+    int cap;            // row walk: staged nonzeros per tile (window + slack, multiple of 4)
+    int rp_cap;         // row walk: staged row pointers per tile (multiple of 4)
+    int general_elems;  // general kernel: products staged per tile
 };
-TileShape tile_shape(int dtype, int variant);
+// avg_row: mean stored entries per row; irregular: general kernel only; overrides: 0 = none (tuning hooks)
+TileShape tile_shape(int dtype, int itype, double avg_row, bool irregular, int lanes_override, int window_override);
+size_t rowwalk_smem_bytes(int dtype, int itype, const TileShape& shape);
 
 struct SpmvLaunch {
     int dtype, itype;
@@ -46,15 +49,16 @@ struct SpmvLaunch {
 
 cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles,
                                cudaStream_t st);
-// *count_out (device, pre-zeroed) += rows whose successor has the same length and first column + 1
-cudaError_t launch_banded_stat(int itype, const void* rowptr, const void* colval, i64 nrows, unsigned long long* count_out, cudaStream_t st);
+// cls[t] = 0 (no rows), 1 (row-walk kernel), 2 (general kernel)
+cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int cap, int rp_cap, unsigned char* cls, cudaStream_t st);
 // rows longer than threshold: writes their local row ids (ascending not guaranteed) into rows_out (capacity cap), count via *count_out (device)
 cudaError_t launch_find_long_rows(int itype, const void* rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
                                   unsigned long long* count_out, cudaStream_t st);
 // flags[t] = 1 iff tile t references a column outside [own_lo, own_lo+own_n)
 cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n,
                                   unsigned char* flags, cudaStream_t st);
-cudaError_t launch_spmv_tiles(const SpmvLaunch& L, cudaStream_t st);
+cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 1
+cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 2
 
 struct LongRowsLaunch {
     int dtype, itype;

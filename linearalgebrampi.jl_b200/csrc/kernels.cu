@@ -2,22 +2,28 @@
 //
 // The arithmetic replaces the reference's one-work-item-per-row KernelAbstractions kernel
 // (_spmv_kernel!, src/sparse.jl:2055-2066) and its gather kernel (_gather_kernel!, src/vectors.jl:174-177).
-// SpMV is HBM-bound (0.10-0.37 flop/B): no tensor cores; the design goals are
-//   * every byte of nzval / colval read exactly once with 128-bit, fully coalesced, streaming (evict-first) loads:
-//     consecutive NONZEROS (not rows) are assigned to consecutive lanes;
-//   * x read through the read-only path (L1/L2 resident for stencil-like column locality);
-//   * products staged in shared memory, then reduced per row by 1, 2, 4, ... 32 lanes chosen per tile from the
-//     mean row length (thread- / sub-warp- / warp-per-row), a warp-per-row streaming path for tiles whose rows do
-//     not fit, and a split (chunk + ordered partial sums, no atomics) path for very long power-law rows;
-//   * the reference's 1-based Int32/Int64 arrays are consumed as they are (no conversion pass, no private copy).
-// With one lane per row the per-row sum runs left to right over products rounded separately from the adds, i.e.
-// bit-identical to the reference's `acc += nzval[j]*x[colval[j]]` (no FMA contraction) for rows of <= 12 entries.
+// SpMV is HBM-bound (0.10-0.37 flop/B): no tensor cores.  The local rows are cut into TILES (the rows whose first
+// stored entry lies in one window of the nonzero stream); every tile is classified once per matrix:
+//   * row-walk tiles (stencil-like: balanced rows) -> spmv_rowwalk_kernel: the tile's colval / nzval / rowptr slices
+//     are staged by three bulk asynchronous copies (1-D TMA, evict-first in L2), then G lanes per row walk the staged
+//     row and gather x through the read-only path; lanes of a warp own consecutive rows, so the gathers coalesce;
+//   * general tiles -> spmv_tile_kernel: 128-bit streaming loads of consecutive NONZEROS per lane, products staged in
+//     shared memory, per-row reduction by 1..32 lanes, warp-per-row for rows too long to stage;
+//   * rows above the split threshold (power-law tails) -> chunk + ordered partial sums, no atomics.
+// The reference's 1-based Int32/Int64 arrays are consumed as they are (no conversion pass, no private copy).
+// With one lane per row the sum runs left to right over products rounded separately from the adds, i.e. it is
+// bit-identical to the reference's `acc += nzval[j]*x[colval[j]]` (no FMA contraction).
 #include <cuda_runtime.h>
 
 #include <cstdint>
 #include <cstdlib>
+#include <mutex>
 
 #include "device.h"
+
+#ifndef HPCLA_WALK_PRED
+#define HPCLA_WALK_PRED 0  // 1: predicated 4-wide batches in the row walk (A/B knob)
+#endif
 
 namespace hpcla {
 
@@ -104,27 +110,16 @@ __device__ __forceinline__ void st_y(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_y(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_y(cplx* p, cplx v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
 
-// per element type: CTA size, 4-nonzero groups per lane and round (variant 1), resident CTAs per SM aimed at (variant 2)
+// general kernel, per element type: CTA size and 4-nonzero groups per lane and round
 template <class T> struct TileCfg;
 template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2; };
 template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2; };
 template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1; };
-constexpr int TMA_RP_CAP = 640;  // staged row pointers per tile (tiles with more rows read rowptr from global memory)
-constexpr int TMA_SLACK = 256;   // staged nonzeros beyond the chunk (rows may run past the window)
-// shared memory of one variant-2 CTA and the resident CTAs per SM it allows (227 KB usable, at most 2048 threads)
-template <class T, class Ti>
-constexpr size_t tma_smem_bytes() {
-    return 16 + 32 * sizeof(T) + sizeof(Ti) * TMA_RP_CAP + (size_t)(TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4 + TMA_SLACK) * (sizeof(Ti) + sizeof(T));
-}
-template <class T> struct RegCap { static constexpr int CTAS = 8; };       // 32 registers per thread
-template <> struct RegCap<double> { static constexpr int CTAS = 7; };      // 36
-template <> struct RegCap<cplx> { static constexpr int CTAS = 5; };        // 48 (16-byte values)
-template <class T, class Ti, bool GHOST>
-constexpr int tma_min_ctas() {
-    int by_smem = (int)((227 * 1024) / (tma_smem_bytes<T, Ti>() + 1024));
-    int cap = RegCap<T>::CTAS - (GHOST ? 1 : 0);
-    return by_smem < cap ? by_smem : cap;
-}
+// row-walk kernel: CTA size, and the resident CTAs per SM the register allocation aims at
+constexpr int ROW_THREADS = 256;
+template <class T> struct RowCfg { static constexpr int CTAS = 8; };   // 32 registers per thread
+template <> struct RowCfg<double> { static constexpr int CTAS = 7; };  // 36
+template <> struct RowCfg<cplx> { static constexpr int CTAS = 5; };    // 48 (16-byte values)
 
 // x addressing: own columns are read straight from x.v (no local copy into `gathered`), ghosts from `gathered`.
 template <class T>
@@ -263,10 +258,10 @@ __global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Variant 2 (default): TMA-staged tiles.
+// Row-walk kernel: TMA-staged tiles.
 // One elected thread issues three bulk asynchronous copies (cp.async.bulk, the 1-D TMA path: global -> shared through
-// L2, bypassing the LSU/L1 wavefront pipeline that bounded variant 1, evict-first in L2) for the tile's slice of
-// colval, nzval and rowptr, completing on an mbarrier.  Then G lanes per row walk the staged row: with one lane per
+// L2, bypassing the LSU/L1 wavefront pipeline that bounds the general kernel, evict-first in L2) for the tile's slice
+// of colval, nzval and rowptr, completing on an mbarrier.  Then G lanes per row walk the staged row: with one lane per
 // row, consecutive lanes handle consecutive ROWS, so for banded / stencil matrices the x gathers of one warp
 // instruction hit consecutive addresses (coalesced), and the row is summed left to right exactly like the reference.
 // ------------------------------------------------------------------------------------------------------------------
@@ -315,9 +310,9 @@ __device__ __forceinline__ T block_sum(T v, T* sh /* [32] */) {
     return r;  // valid in warp 0
 }
 
-// Mode A — row walk: G lanes per row (interleaved: lane g takes entries g, g+G, ...), operands read from shared
-// memory, x gathered per entry.  Lanes of a warp own consecutive rows, so on banded matrices the gathers of one warp
-// instruction fall into a few contiguous runs (coalesced).  G = 1 sums left to right: the reference's order, bit for bit.
+// Row walk: G lanes per row (interleaved: lane g takes entries g, g+G, ...), operands read from shared memory, x
+// gathered per entry.  Lanes of a warp own consecutive rows, so on banded matrices the gathers of one warp instruction
+// fall into a few contiguous runs (coalesced).  G = 1 sums left to right: the reference's order, bit for bit.
 template <class T, class Ti, int THREADS, int G, bool GHOST>
 __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const Ti* rp, i64 rp_off, const XView<T>& xv, T* __restrict__ y, i64 r0,
                                           i64 r1, i64 s4, int tid) {
@@ -331,6 +326,19 @@ __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const T
             const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
             const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
             int k = b + lane;
+#if HPCLA_WALK_PRED
+            for (; k < e; k += 4 * G) {  // 4 predicated gathers in flight per lane, then the adds in order
+                T p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + u * G;
+                    p[u] = (kk < e) ? el_mul(sval[kk], x_at<GHOST, T, Ti>(xv, scol[kk])) : el_zero(T());
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k + u * G < e) acc = el_add(acc, p[u]);
+            }
+#else
             for (; k + 3 * G < e; k += 4 * G) {  // 4 independent gathers in flight per lane, then the adds in order
                 T p[4];
 #pragma unroll
@@ -339,6 +347,7 @@ __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const T
                 for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
             }
             for (; k < e; k += G) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
+#endif
         }
         if (G > 1) {
 #pragma unroll
@@ -348,59 +357,15 @@ __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const T
     }
 }
 
-// Mode B, step 2 — per-row sums of the staged products by G cooperating lanes (G = 1: reference order)
-template <class T, class Ti, int THREADS, int G>
-__device__ __forceinline__ void rows_sum(const T* prod, const Ti* rp, i64 rp_off, T* __restrict__ y, i64 r0, i64 r1, i64 s4, int tid) {
-    constexpr int RPP = THREADS / G;
-    const int lane = tid % G;
-    for (i64 base = r0; base < r1; base += RPP) {
-        const i64 r = base + tid / G;
-        const bool valid = r < r1;
-        T acc = el_zero(T());
-        if (valid) {
-            const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
-            const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
-            for (int k = b + lane; k < e; k += G) acc = el_add(acc, prod[k]);
-        }
-        if (G > 1) {
-#pragma unroll
-            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
-        }
-        if (valid && lane == 0) st_y(y + r, acc);
-    }
-}
-
-__device__ __forceinline__ void ld4_shared(const int* p, int (&v)[4]) {
-    int4 t = *reinterpret_cast<const int4*>(p);
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-}
-__device__ __forceinline__ void ld4_shared(const long long* p, long long (&v)[4]) {
-    longlong2 a = reinterpret_cast<const longlong2*>(p)[0], b = reinterpret_cast<const longlong2*>(p)[1];
-    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
-}
-__device__ __forceinline__ void ld4_shared(const float* p, float (&v)[4]) {
-    float4 t = *reinterpret_cast<const float4*>(p);
-    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
-}
-__device__ __forceinline__ void ld4_shared(const double* p, double (&v)[4]) {
-    double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
-    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
-}
-__device__ __forceinline__ void ld4_shared(const cplx* p, cplx (&v)[4]) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        double2 t = reinterpret_cast<const double2*>(p)[k];
-        v[k] = cplx{t.x, t.y};
-    }
-}
-
-template <class T, class Ti, int THREADS, bool GHOST>
-__global__ void __launch_bounds__(THREADS, tma_min_ctas<T, Ti, GHOST>()) spmv_tile_tma_kernel(const TileArgs<T, Ti> a, int cap, i64 rowptr_len) {
+// One CTA per ROW-WALK tile (classified at set-up: every row of the tile is completely staged, its row pointers fit,
+// and the lanes are well used).  Nothing but: three bulk copies, one wait, the walk.
+template <class T, class Ti, int G, bool GHOST>
+__global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - (GHOST ? 1 : 0))
+    spmv_rowwalk_kernel(const TileArgs<T, Ti> a, int cap, int rp_cap, i64 rowptr_len) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    T* red = reinterpret_cast<T*>(smem_raw + 16);  // [32] block-reduction scratch
-    Ti* srp = reinterpret_cast<Ti*>(smem_raw + 16 + 32 * sizeof(T));
-    Ti* scol = srp + TMA_RP_CAP;
+    Ti* srp = reinterpret_cast<Ti*>(smem_raw + 16);
+    Ti* scol = srp + rp_cap;
     T* sval = reinterpret_cast<T*>(scol + cap);
     const int tid = threadIdx.x;
     const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
@@ -410,24 +375,16 @@ __global__ void __launch_bounds__(THREADS, tma_min_ctas<T, Ti, GHOST>()) spmv_ti
     if (r1 <= r0) return;
     const i64 s = d0.y, e = d1.y;  // 0-based nonzero range of the tile's rows
     const i64 s4 = s & ~(i64)3;    // 16-byte aligned for every element width
-    const i64 n_all = e - s4;
-    // Rows start inside the tile's window, so only the LAST row can run past it: everything up to `cap` elements is
-    // staged; an overrunning last row is finished from global memory by the whole CTA.
-    const bool overrun = n_all > (i64)cap;
-    const int n_st = overrun ? cap : (int)n_all;
+    const int n_st = (int)(e - s4);  // <= cap (classification)
     const i64 avail = a.nnz_total - s4;
     const int n_bulk = (int)((((i64)n_st + 3) & ~(i64)3) <= avail ? (((i64)n_st + 3) & ~(i64)3) : (avail & ~(i64)3));
     const i64 rp0 = r0 & ~(i64)3;
-    const i64 rp_need = r1 + 1 - rp0;  // entries rp0 .. r1
-    const bool rp_smem = rp_need <= TMA_RP_CAP;
+    const int rp_need = (int)(r1 + 1 - rp0);  // entries rp0 .. r1, <= rp_cap (classification)
     const i64 rp_avail = rowptr_len - rp0;
-    const int rp_bulk = rp_smem ? (int)(((rp_need + 3) & ~(i64)3) <= rp_avail ? ((rp_need + 3) & ~(i64)3) : (rp_avail & ~(i64)3)) : 0;
+    const int rp_bulk = (int)((((i64)rp_need + 3) & ~(i64)3) <= rp_avail ? (((i64)rp_need + 3) & ~(i64)3) : (rp_avail & ~(i64)3));
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
         const uint64_t pol = l2_evict_first_policy();
         mbar_expect_tx(bar, (uint32_t)n_bulk * (uint32_t)(sizeof(Ti) + sizeof(T)) + (uint32_t)rp_bulk * (uint32_t)sizeof(Ti));
         if (n_bulk > 0) {
@@ -437,87 +394,14 @@ __global__ void __launch_bounds__(THREADS, tma_min_ctas<T, Ti, GHOST>()) spmv_ti
         if (rp_bulk > 0) bulk_g2s(srp, a.rowptr + rp0, (uint32_t)rp_bulk * (uint32_t)sizeof(Ti), bar, pol);
     }
     // tails: the <= 3 elements a 16-byte copy would read past the end of an array (last tile of the matrix only)
-    for (int k = n_bulk + tid; k < n_st; k += THREADS) {
+    for (int k = n_bulk + tid; k < n_st; k += ROW_THREADS) {
         scol[k] = a.colval[s4 + k];
         sval[k] = a.nzval[s4 + k];
     }
-    if (rp_smem)
-        for (int k = rp_bulk + tid; k < (int)rp_need; k += THREADS) srp[k] = a.rowptr[rp0 + k];
+    for (int k = rp_bulk + tid; k < rp_need; k += ROW_THREADS) srp[k] = a.rowptr[rp0 + k];
+    __syncthreads();  // barrier initialised (and the tails written) before anyone waits
     mbar_wait(bar, 0);
-    __syncthreads();
-
-    const Ti* rp = rp_smem ? srp : a.rowptr;
-    const i64 rp_off = rp_smem ? rp0 : 0;
-    const i64 r_st = overrun ? r1 - 1 : r1;  // rows [r0, r_st) are completely staged
-    const i64 nrows_st = r_st - r0;
-
-    // Mode A needs a banded pattern (next row: same length, columns shifted by one); lanes per row fill the CTA
-    bool mode_a = false;
-    if (!overrun && nrows_st >= 8) {
-        int ok = 0;
-        if (tid < nrows_st - 1) {
-            const i64 r = r0 + tid;
-            const i64 b0 = (i64)rp[r - rp_off], b1 = (i64)rp[r - rp_off + 1], b2 = (i64)rp[r - rp_off + 2];
-            ok = (b1 - b0 == b2 - b1) && (b1 > b0) && (scol[b0 - 1 - s4] + 1 == scol[b1 - 1 - s4]);
-        }
-        const int cnt = __syncthreads_count(ok);
-        const int checked = (int)(nrows_st < THREADS ? nrows_st : THREADS) - 1;
-        mode_a = 4 * cnt >= 3 * checked;
-    }
-    if (mode_a) {
-        int G = 1;
-        while (G < 8 && nrows_st * (2 * G) <= THREADS) G *= 2;
-        switch (G) {
-            case 1: rows_walk<T, Ti, THREADS, 1, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
-            case 2: rows_walk<T, Ti, THREADS, 2, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
-            case 4: rows_walk<T, Ti, THREADS, 4, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
-            default: rows_walk<T, Ti, THREADS, 8, GHOST>(scol, sval, rp, rp_off, a.xv, a.y, r0, r_st, s4, tid); break;
-        }
-        return;
-    }
-    // Mode B, step 1 — products in place: consecutive lanes take consecutive nonzeros (4 each), all gathers of a lane
-    // are independent, so irregular columns get the most memory-level parallelism
-    for (int i = tid * 4; i < n_st; i += THREADS * 4) {
-        Ti c[4];
-        T v[4], xg[4];
-        ld4_shared(scol + i, c);
-        ld4_shared(sval + i, v);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xg[k] = x_at<GHOST, T, Ti>(a.xv, (i + k < n_st) ? c[k] : (Ti)a.safe_col);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = el_mul(v[k], xg[k]);
-        st4_shared(sval + i, v);
-    }
-    __syncthreads();
-    if (nrows_st > 0) {
-        const i64 e_st = overrun ? (i64)rp[r_st - rp_off] - 1 : e;
-        const i64 avg = (e_st - s) / nrows_st;
-        if (avg <= 12) rows_sum<T, Ti, THREADS, 1>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
-        else if (avg <= 24) rows_sum<T, Ti, THREADS, 2>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
-        else if (avg <= 48) rows_sum<T, Ti, THREADS, 4>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
-        else if (avg <= 96) rows_sum<T, Ti, THREADS, 8>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
-        else if (avg <= 192) rows_sum<T, Ti, THREADS, 16>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
-        else rows_sum<T, Ti, THREADS, 32>(sval, rp, rp_off, a.y, r0, r_st, s4, tid);
-    }
-    if (overrun) {
-        // the last row: staged products first, the rest straight from global memory (coalesced, streaming)
-        const i64 r = r1 - 1;
-        const i64 b = (i64)rp[r - rp_off] - 1;  // absolute 0-based start
-        if (e - b <= a.long_threshold) {
-            T acc0 = el_zero(T()), acc1 = el_zero(T());
-            for (i64 k = b - s4 + tid; k < (i64)n_st; k += THREADS) acc0 = el_add(acc0, sval[k]);
-            i64 k = s4 + n_st + tid;
-            for (; k + THREADS < e; k += 2 * THREADS) {
-                const Ti c0 = ld_stream(a.colval + k), c1 = ld_stream(a.colval + k + THREADS);
-                const T v0 = ld_stream(a.nzval + k), v1 = ld_stream(a.nzval + k + THREADS);
-                acc0 = el_add(acc0, el_mul(v0, x_at<GHOST, T, Ti>(a.xv, c0)));
-                acc1 = el_add(acc1, el_mul(v1, x_at<GHOST, T, Ti>(a.xv, c1)));
-            }
-            if (k < e) acc0 = el_add(acc0, el_mul(ld_stream(a.nzval + k), x_at<GHOST, T, Ti>(a.xv, ld_stream(a.colval + k))));
-            const T tot = block_sum(el_add(acc0, acc1), red);
-            if (tid == 0) st_y(a.y + r, tot);
-        }
-    }
+    rows_walk<T, Ti, ROW_THREADS, G, GHOST>(scol, sval, srp, rp0, a.xv, a.y, r0, r1, s4, tid);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -587,19 +471,6 @@ __global__ void build_tiles_kernel(const Ti* __restrict__ rowptr, i64 nrows, int
     tiles[k].nnz = (i64)rowptr[r] - 1;
 }
 
-// rows whose successor has the same length and its first column shifted by one ("banded"): picks the kernel variant
-template <class Ti>
-__global__ void __launch_bounds__(256) banded_stat_kernel(const Ti* __restrict__ rowptr, const Ti* __restrict__ colval, i64 nrows, unsigned long long* count) {
-    const i64 r = (i64)blockIdx.x * 256 + threadIdx.x;
-    int ok = 0;
-    if (r + 1 < nrows) {
-        const i64 b0 = (i64)rowptr[r], b1 = (i64)rowptr[r + 1], b2 = (i64)rowptr[r + 2];
-        ok = (b1 - b0 == b2 - b1) && (b1 > b0) && (colval[b0 - 1] + 1 == colval[b1 - 1]);
-    }
-    const int cnt = __syncthreads_count(ok);
-    if (threadIdx.x == 0 && cnt) atomicAdd(count, (unsigned long long)cnt);
-}
-
 template <class Ti>
 __global__ void find_long_rows_kernel(const Ti* __restrict__ rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
                                       unsigned long long* count) {
@@ -620,6 +491,35 @@ __global__ void __launch_bounds__(256) classify_tiles_kernel(const Ti* __restric
     for (i64 k = b + threadIdx.x; k < e; k += 256) ghost |= ((unsigned long long)((i64)colval[k] - own_lo) >= own_n);
     ghost = __syncthreads_or(ghost);
     if (threadIdx.x == 0) flags[t] = ghost ? 1 : 0;
+}
+
+// Kernel class of every tile, one warp per tile: 0 = no row starts in the tile's window, 1 = row walk (all rows
+// completely staged within `cap` nonzeros and `rp_cap` row pointers, and mean row length >= half the longest, i.e. the
+// lanes of the walk are well used), 2 = general kernel.
+template <class Ti>
+__global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ rowptr, const TileDesc* __restrict__ tiles, i64 ntiles, int cap, int rp_cap,
+                                                         unsigned char* cls) {
+    const i64 t = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= ntiles) return;
+    const i64 r0 = tiles[t].row, r1 = tiles[t + 1].row, s = tiles[t].nnz, e = tiles[t + 1].nnz;
+    if (r1 <= r0) {
+        if (lane == 0) cls[t] = 0;
+        return;
+    }
+    i64 maxlen = 0;
+    for (i64 r = r0 + lane; r < r1; r += 32) {
+        const i64 len = (i64)rowptr[r + 1] - (i64)rowptr[r];
+        maxlen = len > maxlen ? len : maxlen;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const i64 o = __shfl_xor_sync(0xffffffffu, maxlen, m);
+        maxlen = o > maxlen ? o : maxlen;
+    }
+    const bool fits = (e - (s & ~(i64)3)) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap;
+    const bool balanced = 2 * (e - s) >= (r1 - r0) * maxlen;
+    if (lane == 0) cls[t] = (fits && balanced && e > s) ? 1 : 2;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -760,20 +660,50 @@ __global__ void cg_update_p_kernel(i64 n, const T* __restrict__ r, T* __restrict
 // host-side launchers
 // ==================================================================================================================
 
+// Tile shape of one matrix.  Row walk: G lanes per row and a window of about (256 / G) mean-length rows, G the
+// smallest power of two for which a tile's operands stay within the shared-memory budget; the general kernel stages
+// products for the same tiles.  `irregular` (most nonzeros in tiles the row walk cannot take): the general kernel's
+// own shape.
 template <class T>
-static TileShape shape_of(int variant) {
+static TileShape shape_of(int itype, double avg_row, bool irregular, int lanes_override, int window_override) {
     TileShape s;
-    s.threads = TileCfg<T>::THREADS;
-    s.chunk = TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4;
-    s.variant = variant;
-    s.window = s.chunk - 64;
-    s.smem_elems = s.chunk + (s.variant == 1 ? 512 : TMA_SLACK);
+    s.threads = ROW_THREADS;
+    const int chunk = TileCfg<T>::THREADS * TileCfg<T>::GROUPS * 4;
+    const size_t per_nz = sizeof(T) + (itype == HPCLA_I32 ? 4 : 8);
+    if (irregular) {
+        s.lanes = 0;
+        s.window = chunk - 64;
+        s.cap = 0;
+        s.rp_cap = 0;
+        s.general_elems = chunk + 512;
+    } else {
+        // measured on B200 (profiles/r1d_tune_*.txt): 27-point rows want ~70 KB tiles (G = 2: 128 rows, 3 CTAs per SM),
+        // 7-point rows fit one row per thread in 21 KB (7 CTAs per SM)
+        const double budget = 72.0 * 1024;
+        int G = 1;
+        while (G < 32 && (ROW_THREADS / G) * avg_row * (double)per_nz > budget) G *= 2;
+        if (lanes_override == 1 || lanes_override == 2 || lanes_override == 4 || lanes_override == 8 || lanes_override == 16 || lanes_override == 32)
+            G = lanes_override;
+        s.lanes = G;
+        double w = (ROW_THREADS / G) * (avg_row > 1.0 ? avg_row : 1.0);
+        const double wmax = budget / (double)per_nz;
+        if (w > wmax) w = wmax;
+        s.window = ((int)w + 3) & ~3;
+        if (s.window < 256) s.window = 256;
+        if (window_override >= 64) s.window = window_override & ~3;
+        int slack = ((int)(4 * avg_row) + 31) & ~31;
+        slack = slack < 64 ? 64 : slack > 512 ? 512 : slack;
+        s.cap = s.window + slack;
+        s.rp_cap = (2 * (ROW_THREADS / G) + 8 + 3) & ~3;
+        s.general_elems = s.cap + 256;
+    }
+    if (window_override >= 64 && irregular && window_override <= s.general_elems - 8) s.window = window_override & ~3;
     return s;
 }
-TileShape tile_shape(int dtype, int variant) {
-    if (dtype == HPCLA_F32) return shape_of<float>(variant);
-    if (dtype == HPCLA_F64) return shape_of<double>(variant);
-    return shape_of<cplx>(variant);
+TileShape tile_shape(int dtype, int itype, double avg_row, bool irregular, int lanes_override, int window_override) {
+    if (dtype == HPCLA_F32) return shape_of<float>(itype, avg_row, irregular, lanes_override, window_override);
+    if (dtype == HPCLA_F64) return shape_of<double>(itype, avg_row, irregular, lanes_override, window_override);
+    return shape_of<cplx>(itype, avg_row, irregular, lanes_override, window_override);
 }
 
 static inline int blocks_for(i64 n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -786,11 +716,11 @@ cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz
     return cudaGetLastError();
 }
 
-cudaError_t launch_banded_stat(int itype, const void* rowptr, const void* colval, i64 nrows, unsigned long long* count_out, cudaStream_t st) {
-    if (nrows < 2) return cudaSuccess;
-    const int blocks = blocks_for(nrows, 256);
-    if (itype == HPCLA_I32) banded_stat_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, (const int*)colval, nrows, count_out);
-    else banded_stat_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, (const long long*)colval, nrows, count_out);
+cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int cap, int rp_cap, unsigned char* cls, cudaStream_t st) {
+    if (ntiles == 0) return cudaSuccess;
+    const int blocks = blocks_for(ntiles, 8);
+    if (itype == HPCLA_I32) tile_class_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, tiles, ntiles, cap, rp_cap, cls);
+    else tile_class_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, tiles, ntiles, cap, rp_cap, cls);
     return cudaGetLastError();
 }
 
@@ -823,10 +753,7 @@ static XView<T> make_xview(const void* x_own, const void* gathered, i64 own_lo, 
 
 
 template <class T, class Ti>
-static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
-    if (L.n_launch <= 0) return cudaSuccess;
-    constexpr int THREADS = TileCfg<T>::THREADS, GROUPS = TileCfg<T>::GROUPS;
-    const TileShape& sh = L.shape;
+static TileArgs<T, Ti> tile_args(const SpmvLaunch& L) {
     TileArgs<T, Ti> a;
     a.rowptr = (const Ti*)L.rowptr;
     a.colval = (const Ti*)L.colval;
@@ -838,31 +765,82 @@ static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
     a.nnz_total = L.nnz;
     a.long_threshold = L.long_threshold;
     a.safe_col = L.own_n > 0 ? L.own_lo : 1;
-    if (sh.variant == 1) {
-        const size_t smem = (size_t)sh.smem_elems * sizeof(T);
-        if (L.has_ghost) spmv_tile_kernel<T, Ti, THREADS, GROUPS, true><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
-        else spmv_tile_kernel<T, Ti, THREADS, GROUPS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems);
-        return cudaGetLastError();
-    }
-    const size_t smem = tma_smem_bytes<T, Ti>();
-    static bool configured[2][64] = {};  // per instantiation, per device: function attributes are per device
+    return a;
+}
+
+// Opt-in dynamic shared memory per kernel instantiation and device (function attributes are per device).  The limit
+// only ever grows: rank-threads of one process share the attribute and may ask for different sizes.
+// carveout: prefer the maximum shared-memory carveout (row walk: x is gathered with coalesced accesses and needs
+// little L1); the general kernel keeps the driver's default split, its scattered gathers live on L1.
+template <auto Kernel>
+static cudaError_t ensure_smem(size_t smem, bool carveout) {
+    static size_t configured[64] = {};
+    static bool carved[64] = {};
+    static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
-    bool& done = configured[L.has_ghost ? 1 : 0][dev & 63];
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = configured[dev & 63];
+    if (have < smem && smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        have = smem;
+    }
+    if (carveout && !carved[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+        carved[dev & 63] = true;
+    }
+    return cudaSuccess;
+}
+
+size_t rowwalk_smem_bytes(int dtype, int itype, const TileShape& sh) {
+    const size_t ts = dtype == HPCLA_F32 ? 4 : dtype == HPCLA_F64 ? 8 : 16, is = itype == HPCLA_I32 ? 4 : 8;
+    return 16 + is * (size_t)sh.rp_cap + (size_t)sh.cap * (is + ts);
+}
+
+template <class T, class Ti, int G>
+static cudaError_t rowwalk_launch(const SpmvLaunch& L, const TileArgs<T, Ti>& a, size_t smem, cudaStream_t st) {
+    cudaError_t e;
     if (L.has_ghost) {
-        if (!done) {
-            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            done = true;
-        }
-        spmv_tile_tma_kernel<T, Ti, THREADS, true><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems, L.nrows + 1);
+        if ((e = ensure_smem<spmv_rowwalk_kernel<T, Ti, G, true>>(smem, true)) != cudaSuccess) return e;
+        spmv_rowwalk_kernel<T, Ti, G, true><<<L.n_launch, ROW_THREADS, smem, st>>>(a, L.shape.cap, L.shape.rp_cap, L.nrows + 1);
     } else {
-        if (!done) {
-            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(spmv_tile_tma_kernel<T, Ti, THREADS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            done = true;
-        }
-        spmv_tile_tma_kernel<T, Ti, THREADS, false><<<L.n_launch, THREADS, smem, st>>>(a, sh.smem_elems, L.nrows + 1);
+        if ((e = ensure_smem<spmv_rowwalk_kernel<T, Ti, G, false>>(smem, true)) != cudaSuccess) return e;
+        spmv_rowwalk_kernel<T, Ti, G, false><<<L.n_launch, ROW_THREADS, smem, st>>>(a, L.shape.cap, L.shape.rp_cap, L.nrows + 1);
+    }
+    return cudaGetLastError();
+}
+
+template <class T, class Ti>
+static cudaError_t spmv_rowwalk_typed(const SpmvLaunch& L, cudaStream_t st) {
+    if (L.n_launch <= 0) return cudaSuccess;
+    const TileArgs<T, Ti> a = tile_args<T, Ti>(L);
+    const size_t smem = rowwalk_smem_bytes(L.dtype, L.itype, L.shape);
+    switch (L.shape.lanes) {
+        case 1: return rowwalk_launch<T, Ti, 1>(L, a, smem, st);
+        case 2: return rowwalk_launch<T, Ti, 2>(L, a, smem, st);
+        case 4: return rowwalk_launch<T, Ti, 4>(L, a, smem, st);
+        case 8: return rowwalk_launch<T, Ti, 8>(L, a, smem, st);
+        case 16: return rowwalk_launch<T, Ti, 16>(L, a, smem, st);
+        case 32: return rowwalk_launch<T, Ti, 32>(L, a, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <class T, class Ti>
+static cudaError_t spmv_general_typed(const SpmvLaunch& L, cudaStream_t st) {
+    if (L.n_launch <= 0) return cudaSuccess;
+    constexpr int THREADS = TileCfg<T>::THREADS, GROUPS = TileCfg<T>::GROUPS;
+    const TileArgs<T, Ti> a = tile_args<T, Ti>(L);
+    const size_t smem = (size_t)L.shape.general_elems * sizeof(T);
+    cudaError_t e;
+    if (L.has_ghost) {
+        if ((e = ensure_smem<spmv_tile_kernel<T, Ti, THREADS, GROUPS, true>>(smem, false)) != cudaSuccess) return e;
+        spmv_tile_kernel<T, Ti, THREADS, GROUPS, true><<<L.n_launch, THREADS, smem, st>>>(a, L.shape.general_elems);
+    } else {
+        if ((e = ensure_smem<spmv_tile_kernel<T, Ti, THREADS, GROUPS, false>>(smem, false)) != cudaSuccess) return e;
+        spmv_tile_kernel<T, Ti, THREADS, GROUPS, false><<<L.n_launch, THREADS, smem, st>>>(a, L.shape.general_elems);
     }
     return cudaGetLastError();
 }
@@ -878,7 +856,8 @@ static cudaError_t spmv_tiles_typed(const SpmvLaunch& L, cudaStream_t st) {
         return cudaErrorInvalidValue;                                                                  \
     } while (0)
 
-cudaError_t launch_spmv_tiles(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_tiles_typed, L, L, st); }
+cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_rowwalk_typed, L, L, st); }
+cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_general_typed, L, L, st); }
 
 template <class T, class Ti>
 static cudaError_t long_rows_typed(const LongRowsLaunch& L, cudaStream_t st) {

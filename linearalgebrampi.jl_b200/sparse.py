@@ -346,7 +346,10 @@ def spmv_info(A: HPCSparseMatrix, x: HPCVector) -> Dict[str, int]:
     _lib.check(L.hpcla_spmv_info(op, ctypes.byref(ni), ctypes.byref(nb), ctypes.byref(xin), ctypes.byref(sc)))
     nt, nl, var = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
     _lib.check(L.hpcla_csr_info(_csr_handle(A), ctypes.byref(nt), ctypes.byref(nl), ctypes.byref(var)))
-    return {"tiles": nt.value, "long_rows": nl.value, "kernel_variant": var.value, "interior_tiles": ni.value, "boundary_tiles": nb.value,
+    nr, ng, ne, win = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
+    _lib.check(L.hpcla_csr_tile_classes(_csr_handle(A), ctypes.byref(nr), ctypes.byref(ng), ctypes.byref(ne), ctypes.byref(win)))
+    return {"tiles": nt.value, "long_rows": nl.value, "lanes_per_row": var.value, "rowwalk_tiles": nr.value, "general_tiles": ng.value,
+            "empty_tiles": ne.value, "tile_window": win.value, "interior_tiles": ni.value, "boundary_tiles": nb.value,
             "x_in_place": xin.value, "sends_contiguous": sc.value, "launches": int(L.hpcla_spmv_launch_count(op))}
 
 

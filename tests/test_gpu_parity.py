@@ -218,7 +218,9 @@ def test_synthetic_stencils(kind, N, T, P):
     for y, yT, info in res:
         assert relerr(y, y_ref) <= TOL[np.dtype(T)] and relerr(yT, yT_ref) <= TOL[np.dtype(T)]
         if kind in (0, 1):
-            assert np.array_equal(y, y_ref), "short-row path must be bit-identical to the reference's summation order"
+            assert info["lanes_per_row"] == 1, info
+            assert np.array_equal(y, y_ref), "one lane per row must be bit-identical to the reference's summation order"
+            assert info["rowwalk_tiles"] > 0
         assert info["x_in_place"] == 1 and info["sends_contiguous"] == 1
         if P > 1:
             assert info["boundary_tiles"] > 0 and info["interior_tiles"] > 0

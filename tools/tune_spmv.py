@@ -50,7 +50,10 @@ def main():
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--reps", type=int, default=100)
     ap.add_argument("--windows", default="")
-    ap.add_argument("--variants", default="1,2")
+    ap.add_argument("--kinds", default="", help="comma list of HPCLA_SPMV_KIND values (general, rowwalk)")
+    ap.add_argument("--lanes", default="", help="comma list of HPCLA_LANES values")
+    ap.add_argument("--sweep", default="", help="comma list of lanes:window pairs")
+    ap.add_argument("--cusparse", action="store_true")
     ap.add_argument("--n", type=int, default=20_000_000, help="rows of the power-law matrix")
     args = ap.parse_args()
     S = la.synth
@@ -64,6 +67,10 @@ def main():
         A = S.stencil_matrix(1, 256, b)
     elif args.workload == "stencil27":
         T, Ti, tn, tin = np.complex128, np.int32, "c128", "i32"
+        b = la.backend_cuda_serial(T, Ti)
+        A = S.stencil_matrix(2, 192, b)
+    elif args.workload == "stencil27-f64":
+        T, Ti, tn, tin = np.float64, np.int32, "f64", "i32"
         b = la.backend_cuda_serial(T, Ti)
         A = S.stencil_matrix(2, 192, b)
     elif args.workload == "laplace2d":
@@ -81,16 +88,44 @@ def main():
     y = la.HPCVector.zeros(b, n)
     bts, fl = algorithmic_bytes_flops(n, n, A.nnz_local, tn, tin, "mul")
     print(f"workload {args.workload}: n={n} nnz={A.nnz_local} bytes={bts/1e9:.3f} GB")
-    configs = [{}] + [{"HPCLA_SPMV_VARIANT": int(v)} for v in args.variants.split(",") if v]
+    configs = [{}]
+    for k in [v for v in args.kinds.split(",") if v]:
+        configs.append({"HPCLA_SPMV_KIND": k})
+    for g in [int(v) for v in args.lanes.split(",") if v]:
+        configs.append({"HPCLA_LANES": g})
+    for spec in [v for v in args.sweep.split(",") if v]:  # lanes:window pairs
+        g, w = spec.split(":")
+        configs.append({"HPCLA_LANES": int(g), "HPCLA_TILE_WINDOW": int(w)})
     for w in [int(v) for v in args.windows.split(",") if v]:
-        configs.append({"HPCLA_SPMV_VARIANT": 2, "HPCLA_TILE_WINDOW": w})
+        configs.append({"HPCLA_TILE_WINDOW": w})
     ref = None
     for env in configs:
         ms, info, res = time_config(A, x, y, env, args.reps)
         if ref is None:
             ref = res
         err = float((res - ref).abs().max() / ref.abs().max())
-        print(f"{str(env):60s} {ms*1e3:9.1f} us  {bts/ms/1e6:8.1f} GB/s  {fl/ms/1e6:8.1f} GFLOP/s  tiles={info['tiles']} variant={info['kernel_variant']} maxrelerr_vs_first={err:.2e}", flush=True)
+        print(f"{str(env):50s} {ms*1e3:9.1f} us  {bts/ms/1e6:8.1f} GB/s  {fl/ms/1e6:8.1f} GFLOP/s  tiles={info['tiles']} G={info['lanes_per_row']} "
+              f"win={info['tile_window']} rowwalk/general={info['rowwalk_tiles']}/{info['general_tiles']} maxrelerr_vs_first={err:.2e}", flush=True)
+    if args.cusparse:
+        # same-box comparator (not part of the reference): cuSPARSE CSR SpMV through torch
+        crow = (A.rowptr_target - 1)
+        col = (A.colval_target - 1)
+        M = torch.sparse_csr_tensor(crow, col, A.nzval, size=(n, n))
+        xv = x.v
+        for _ in range(3):
+            yy = M @ xv
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(3):
+            e0.record()
+            for _ in range(max(args.reps // 4, 5)):
+                yy = M @ xv
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / max(args.reps // 4, 5))
+        err = float((yy - ref).abs().max() / ref.abs().max())
+        print(f"{'cuSPARSE (torch.sparse_csr @ x, allocates y)':50s} {best*1e3:9.1f} us  {bts/best/1e6:8.1f} GB/s  {fl/best/1e6:8.1f} GFLOP/s  maxrelerr_vs_first={err:.2e}", flush=True)
 
 
 if __name__ == "__main__":
