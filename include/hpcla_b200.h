@@ -140,6 +140,13 @@ int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* csr, const hpcla_plan* plan, in
  * of Base.:*(A, x) (src/sparse.jl:2096-2128) and of mul!(y, A, x) (:2019-2037).  d_x = x.v, d_y = y.v (device).
  * NCCL world or nranks == 1: one call does everything (collective).  Enqueue only. */
 int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
+/* Staged multiply for HOST-resident vectors — what the reference's CUDA path does on every call, a host -> device
+ * copy of x, the multiply, a device -> host copy of the result (src/vectors.jl:423, 460; mul! computes on host arrays,
+ * src/sparse.jl:2019-2037) — as one pipelined call: x.v is uploaded in chunks, each block of rows runs as soon as the
+ * prefix of x.v it reads has landed, and its slice of y.v is downloaded while later blocks compute (PCIe both ways at
+ * once).  Equivalent to copy(h_x -> d_x); hpcla_spmv_run(op, d_x, d_y); copy(d_y -> h_y).  h_x / h_y should be pinned.
+ * Enqueue only: h_y is complete once `stream` has been synchronised.  NCCL world or nranks == 1. */
+int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x, void* d_y, void* h_y, void* stream);
 /* Single-process world: call begin on every rank, then finish on every rank. */
 int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
 int hpcla_spmv_finish(hpcla_spmv* op);

@@ -15,7 +15,7 @@ from .backends import (  # noqa: F401
 from .vectors import HPCVector, axpby, compute_partition_hash, dot, norm, uniform_partition  # noqa: F401
 from .sparse import (  # noqa: F401
     HPCSparseMatrix, Transpose, VectorPlan, build_vector_plan, cache_sizes, cg, clear_plan_cache, compute_structural_hash,
-    execute_plan, get_vector_plan, materialize_transpose, matvec, mul, spmv_info, to_backend, transpose, transpose_matvec,
+    execute_plan, get_vector_plan, materialize_transpose, matvec, mul, mul_staged, spmv_info, to_backend, transpose, transpose_matvec,
     vec_adjoint_mul, vec_transpose_mul,
 )
 from . import sparse, synth, vectors, backends  # noqa: F401

@@ -76,6 +76,7 @@ SIGNATURES = {
     "hpcla_csr_destroy": (None, [_vp]),
     "hpcla_spmv_create": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hpcla_spmv_run": (_i, [_vp, _vp, _vp, _vp]),
+    "hpcla_spmv_run_staged": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_spmv_begin": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_finish": (_i, [_vp]),
     "hpcla_spmv_gather": (_i, [_vp, _vp, _vp, _vp]),

@@ -90,6 +90,7 @@ struct hpcla_group {
 struct hpcla_ctx {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t halo_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // staged multiply (created on first use)
     ncclComm_t comm = nullptr;
     bool comm_owned = false;
     hpcla_group* group = nullptr;
@@ -123,6 +124,20 @@ struct Seg {
     i64 src0;         // send only: first 1-based local index
 };
 
+// Staged multiply (host x in, host y out): the rows are cut into blocks of consecutive tiles; block k may run once the
+// prefix of x.v its interior tiles read has landed, and its slice of y goes back while later blocks compute.
+struct HostPipe {
+    bool usable = false;
+    int nb = 0;
+    std::vector<i64> row_at;     // [nb+1] first local row of each block
+    std::vector<int> pos[2][2];  // [nb+1] positions of the block boundaries in each tile list
+    std::vector<int> in_chunk;   // [nb] the x chunk that must have landed before the block runs (-1: none)
+    std::vector<char> late;      // [nb] y slice complete only after the boundary tiles / split long rows
+    std::vector<i64> xchunk;     // [nb+1] element offsets of the x chunks
+    std::vector<cudaEvent_t> ev_in, ev_c;
+    cudaEvent_t ev_start = nullptr, ev_tail = nullptr, ev_done = nullptr;
+};
+
 struct hpcla_spmv {
     hpcla_ctx* ctx = nullptr;
     hpcla_csr* csr = nullptr;
@@ -143,6 +158,8 @@ struct hpcla_spmv {
     i64 *d_local_src = nullptr, *d_local_dst = nullptr;     // only when needed (fallback / gather hook)
     int* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
     int n_list[2][2] = {{0, 0}, {0, 0}};
+    std::vector<int> h_list[2][2];  // host copies (block boundaries of the staged multiply)
+    struct HostPipe* pipe = nullptr;
     cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
     bool halo_recorded = false;
     // in-flight call
@@ -260,6 +277,8 @@ extern "C" void hpcla_ctx_destroy(hpcla_ctx* ctx) {
     if (ctx->comm && ctx->comm_owned) nccl_api()->CommDestroy(ctx->comm);
     if (ctx->group && --ctx->group->refs == 0) delete ctx->group;
     if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     cudaFree(ctx->d_red_scratch);
     cudaFree(ctx->d_red_out);
     cudaFreeHost(ctx->h_red_out);
@@ -297,7 +316,22 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     if (const char* e = getenv("HPCLA_LANES")) lanes_override = atoi(e);
     if (const char* e = getenv("HPCLA_TILE_WINDOW")) window_override = atoi(e);
     if (const char* e = getenv("HPCLA_SPMV_KIND")) kind = (e[0] == 'g') ? 2 : (e[0] == 'r') ? 1 : 0;
-    const double avg_row = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    // typical row length: the most common one (a window of whole typical rows keeps tiles row-aligned), else the mean
+    double avg_row = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    if (nrows > 0 && nnz > 0) {
+        unsigned long long* d_hist = nullptr;
+        std::vector<unsigned long long> hist(1024, 0);
+        CU_TRY(cudaMalloc(&d_hist, sizeof(unsigned long long) * 1024));
+        CU_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * 1024, st));
+        CU_TRY(launch_row_len_hist(itype, d_rowptr, nrows, d_hist, st));
+        CU_TRY(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * 1024, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_hist);
+        int mode = 1;
+        for (int l = 1; l < 1023; ++l)
+            if (hist[(size_t)l] > hist[(size_t)mode]) mode = l;
+        if (2 * hist[(size_t)mode] >= (unsigned long long)nrows) avg_row = (double)mode;  // a clear majority of the rows
+    }
     A->long_threshold = 16384;
     A->chunk_nnz = 16384;
     for (int pass = 0; pass < 2; ++pass) {
@@ -476,7 +510,7 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
             CU_TRY(cudaStreamSynchronize(ctx->halo_stream));
             cudaFree(d_flags);
         }
-        std::vector<int> lists[2][2];
+        std::vector<int> (&lists)[2][2] = op->h_list;
         for (i64 t = 0; t < A->ntiles; ++t) {
             const int c = A->tile_class[(size_t)t];
             if (c) lists[c - 1][flags[(size_t)t] ? 1 : 0].push_back((int)t);
@@ -526,6 +560,14 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
     cudaFree(op->d_local_dst);
     for (int c = 0; c < 2; ++c)
         for (int g = 0; g < 2; ++g) cudaFree(op->d_list[c][g]);
+    if (op->pipe) {
+        for (cudaEvent_t e : op->pipe->ev_in) cudaEventDestroy(e);
+        for (cudaEvent_t e : op->pipe->ev_c) cudaEventDestroy(e);
+        if (op->pipe->ev_start) cudaEventDestroy(op->pipe->ev_start);
+        if (op->pipe->ev_tail) cudaEventDestroy(op->pipe->ev_tail);
+        if (op->pipe->ev_done) cudaEventDestroy(op->pipe->ev_done);
+        delete op->pipe;
+    }
     if (op->ev_x) cudaEventDestroy(op->ev_x);
     if (op->ev_packed) cudaEventDestroy(op->ev_packed);
     if (op->ev_halo) cudaEventDestroy(op->ev_halo);
@@ -549,13 +591,17 @@ static hpcla_spmv* group_peer(const hpcla_spmv* op, int peer) {
 
 // Send half of the exchange, on the halo stream: wait for x, pack what is not contiguous, and (NCCL world) post the
 // grouped send/recv pairs so that ghosts land directly in their segments of `gathered` (no unpack: SURVEY §0.7).
-static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream) {
+static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream, cudaEvent_t x_ready = nullptr) {
     hpcla_ctx* ctx = op->ctx;
     const int dtype = op->csr->dtype;
     const size_t es = dtype_size(dtype);
     cudaStream_t hs = ctx->halo_stream;
-    CU_TRY(cudaEventRecord(op->ev_x, stream));
-    CU_TRY(cudaStreamWaitEvent(hs, op->ev_x, 0));
+    if (x_ready) {  // staged multiply: x.v is complete when the last upload chunk has landed
+        CU_TRY(cudaStreamWaitEvent(hs, x_ready, 0));
+    } else {
+        CU_TRY(cudaEventRecord(op->ev_x, stream));
+        CU_TRY(cudaStreamWaitEvent(hs, op->ev_x, 0));
+    }
     const bool group = ctx->group != nullptr;
     if (group) {
         // my packed buffer may still be read by a peer's copy of the previous multiply
@@ -641,10 +687,13 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
 }
 
 // both kernel classes over the interior (which = 0) or boundary (which = 1) tiles
-static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t stream) {
+// (from, to: positions in the lists, per class; nullptr = the whole lists)
+static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t stream, const int* from = nullptr, const int* to = nullptr) {
     for (int c = 0; c < 2; ++c) {
-        L.tile_list = op->d_list[c][which];
-        L.n_launch = op->n_list[c][which];
+        const int lo = from ? from[c] : 0, hi = to ? to[c] : op->n_list[c][which];
+        L.tile_list = op->d_list[c][which] ? op->d_list[c][which] + lo : nullptr;
+        L.tile_base = lo;  // without a list the list is the identity
+        L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
         if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
         else CU_TRY(launch_spmv_general(L, stream));
@@ -780,6 +829,174 @@ extern "C" int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* 
     int rc = hpcla_spmv_begin(op, d_x, d_y, stream);
     if (rc) return rc;
     return hpcla_spmv_finish(op);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// staged multiply: host x -> x.v, y.v = A * x, y.v -> host y, pipelined over row blocks
+// ---------------------------------------------------------------------------------------------------------------
+static int build_pipe(hpcla_spmv* op) {
+    hpcla_ctx* ctx = op->ctx;
+    const hpcla_csr* A = op->csr;
+    HostPipe* P = new HostPipe();
+    op->pipe = P;
+    if (!ctx->h2d_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    CU_TRY(cudaEventCreateWithFlags(&P->ev_start, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&P->ev_tail, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&P->ev_done, cudaEventDisableTiming));
+    const size_t es = dtype_size(A->dtype);
+    i64 chunk_bytes = 8 << 20;  // measured: 8 MiB chunks give the best PCIe overlap (profiles/r1e_staged_chunks.txt)
+    if (const char* e = getenv("HPCLA_STAGE_CHUNK_KB")) chunk_bytes = std::max<i64>(64, atoll(e)) << 10;
+    const i64 bytes = std::max(op->n_x_local, A->nrows) * (i64)es;
+    int nb = (int)std::min<i64>(64, std::max<i64>(1, (bytes + chunk_bytes - 1) / chunk_bytes));
+    if ((i64)nb > A->ntiles) nb = (int)std::max<i64>(1, A->ntiles);
+    // pipelining needs x.v read in place (own columns straight from x.v) and something to overlap
+    P->usable = op->x_in_place && nb >= 2 && A->nrows > 0 && op->n_x_local > 0;
+    if (!P->usable) return HPCLA_OK;
+    P->nb = nb;
+    // block boundaries in tiles, rows, and list positions
+    std::vector<TileDesc> tiles((size_t)A->ntiles + 1);
+    CU_TRY(cudaMemcpy(tiles.data(), A->d_tiles, sizeof(TileDesc) * tiles.size(), cudaMemcpyDeviceToHost));
+    std::vector<i64> tb((size_t)nb + 1);
+    P->row_at.resize((size_t)nb + 1);
+    for (int k = 0; k <= nb; ++k) {
+        tb[(size_t)k] = (i64)k * A->ntiles / nb;
+        P->row_at[(size_t)k] = k == nb ? A->nrows : tiles[(size_t)tb[(size_t)k]].row;
+    }
+    for (int c = 0; c < 2; ++c)
+        for (int g = 0; g < 2; ++g) {
+            const std::vector<int>& l = op->h_list[c][g];
+            P->pos[c][g].resize((size_t)nb + 1);
+            for (int k = 0; k <= nb; ++k) P->pos[c][g][(size_t)k] = (int)(std::lower_bound(l.begin(), l.end(), (int)tb[(size_t)k]) - l.begin());
+        }
+    // x prefix needed by the interior tiles of each block
+    std::vector<i64> maxcol((size_t)A->ntiles, -1);
+    {
+        i64* d_max = nullptr;
+        CU_TRY(cudaMalloc(&d_max, sizeof(i64) * (size_t)A->ntiles));
+        CU_TRY(launch_tile_maxcol(A->itype, A->d_colval, A->d_tiles, A->ntiles, op->own_lo, op->own_n, d_max, ctx->halo_stream));
+        CU_TRY(cudaMemcpyAsync(maxcol.data(), d_max, sizeof(i64) * maxcol.size(), cudaMemcpyDeviceToHost, ctx->halo_stream));
+        CU_TRY(cudaStreamSynchronize(ctx->halo_stream));
+        cudaFree(d_max);
+    }
+    P->xchunk.resize((size_t)nb + 1);
+    for (int k = 0; k <= nb; ++k) P->xchunk[(size_t)k] = (i64)k * op->n_x_local / nb;
+    P->in_chunk.assign((size_t)nb, -1);
+    P->late.assign((size_t)nb, 0);
+    int running = -1;
+    for (int k = 0; k < nb; ++k) {
+        i64 need = -1;
+        for (int c = 0; c < 2; ++c)
+            for (int q = P->pos[c][0][(size_t)k]; q < P->pos[c][0][(size_t)k + 1]; ++q) need = std::max(need, maxcol[(size_t)op->h_list[c][0][(size_t)q]]);
+        if (need >= 0) {
+            const i64 xi = need + op->own_src0 - 1;  // 0-based index into x.v
+            int j = (int)(std::upper_bound(P->xchunk.begin(), P->xchunk.end(), xi) - P->xchunk.begin()) - 1;
+            j = std::min(std::max(j, 0), nb - 1);
+            running = std::max(running, j);
+        }
+        P->in_chunk[(size_t)k] = running;
+        for (int c = 0; c < 2; ++c)
+            if (P->pos[c][1][(size_t)k + 1] > P->pos[c][1][(size_t)k]) P->late[(size_t)k] = 1;
+    }
+    if (A->nlong > 0) {
+        std::vector<i64> rows((size_t)A->nlong);
+        CU_TRY(cudaMemcpy(rows.data(), A->d_long_rows, sizeof(i64) * rows.size(), cudaMemcpyDeviceToHost));
+        for (i64 r : rows) {
+            const int k = (int)(std::upper_bound(P->row_at.begin(), P->row_at.end(), r) - P->row_at.begin()) - 1;
+            if (k >= 0 && k < nb) P->late[(size_t)k] = 1;
+        }
+    }
+    P->ev_in.resize((size_t)nb);
+    P->ev_c.resize((size_t)nb);
+    for (int k = 0; k < nb; ++k) {
+        CU_TRY(cudaEventCreateWithFlags(&P->ev_in[(size_t)k], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&P->ev_c[(size_t)k], cudaEventDisableTiming));
+    }
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x, void* d_y, void* h_y, void* stream_) {
+    if (!op || (op->n_x_local > 0 && (!h_x || !d_x)) || (op->csr->nrows > 0 && (!h_y || !d_y))) return fail(HPCLA_ERR_ARG, "hpcla_spmv_run_staged: null");
+    if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_run_staged: the previous call was not finished");
+    hpcla_ctx* ctx = op->ctx;
+    if (ctx->group && ctx->nranks > 1 && op->has_peers) return fail(HPCLA_ERR_STATE, "hpcla_spmv_run_staged: needs an NCCL world or a single rank");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const hpcla_csr* A = op->csr;
+    const size_t es = dtype_size(A->dtype);
+    if (!op->pipe) {
+        rc = build_pipe(op);
+        if (rc) return rc;
+    }
+    HostPipe* P = op->pipe;
+    if (!P->usable) {  // nothing to overlap: copy, multiply, copy on the caller's stream
+        if (op->n_x_local > 0) CU_TRY(cudaMemcpyAsync(d_x, h_x, es * (size_t)op->n_x_local, cudaMemcpyHostToDevice, stream));
+        rc = hpcla_spmv_run(op, d_x, d_y, stream);
+        if (rc) return rc;
+        if (A->nrows > 0) CU_TRY(cudaMemcpyAsync(h_y, d_y, es * (size_t)A->nrows, cudaMemcpyDeviceToHost, stream));
+        return HPCLA_OK;
+    }
+    const int nb = P->nb;
+    cudaStream_t in = ctx->h2d_stream, out = ctx->d2h_stream;
+    // x.v and y.v may still be in use by earlier work of the caller's stream
+    CU_TRY(cudaEventRecord(P->ev_start, stream));
+    CU_TRY(cudaStreamWaitEvent(in, P->ev_start, 0));
+    CU_TRY(cudaStreamWaitEvent(out, P->ev_start, 0));
+    for (int j = 0; j < nb; ++j) {
+        const i64 b = P->xchunk[(size_t)j], e = P->xchunk[(size_t)j + 1];
+        if (e > b) CU_TRY(cudaMemcpyAsync((char*)d_x + (size_t)b * es, (const char*)h_x + (size_t)b * es, (size_t)(e - b) * es, cudaMemcpyHostToDevice, in));
+        CU_TRY(cudaEventRecord(P->ev_in[(size_t)j], in));
+    }
+    op->cur_x = d_x;
+    op->cur_y = d_y;
+    op->cur_stream = stream;
+    maybe_persist_x(op, d_x, stream);
+    if (op->has_peers) {
+        rc = exchange_begin(op, d_x, stream, P->ev_in[(size_t)nb - 1]);
+        if (rc) return rc;
+    }
+    SpmvLaunch L;
+    fill_launch(op, L, d_x, d_y);
+    L.has_ghost = false;
+    int waited = -1;
+    for (int k = 0; k < nb; ++k) {
+        if (P->in_chunk[(size_t)k] > waited) {
+            waited = P->in_chunk[(size_t)k];
+            CU_TRY(cudaStreamWaitEvent(stream, P->ev_in[(size_t)waited], 0));
+        }
+        const int from[2] = {P->pos[0][0][(size_t)k], P->pos[1][0][(size_t)k]}, to[2] = {P->pos[0][0][(size_t)k + 1], P->pos[1][0][(size_t)k + 1]};
+        rc = launch_tiles(op, L, 0, stream, from, to);
+        if (rc) return rc;
+        if (!P->late[(size_t)k]) {
+            const i64 r0 = P->row_at[(size_t)k], r1 = P->row_at[(size_t)k + 1];
+            if (r1 > r0) {
+                CU_TRY(cudaEventRecord(P->ev_c[(size_t)k], stream));
+                CU_TRY(cudaStreamWaitEvent(out, P->ev_c[(size_t)k], 0));
+                CU_TRY(cudaMemcpyAsync((char*)h_y + (size_t)r0 * es, (const char*)d_y + (size_t)r0 * es, (size_t)(r1 - r0) * es, cudaMemcpyDeviceToHost, out));
+            }
+        }
+    }
+    // the tail: boundary tiles (need the ghosts) and split long rows (need all of x), then the late slices of y
+    if (waited < nb - 1) CU_TRY(cudaStreamWaitEvent(stream, P->ev_in[(size_t)nb - 1], 0));
+    if (op->has_peers) CU_TRY(cudaStreamWaitEvent(stream, op->ev_halo, 0));
+    fill_launch(op, L, d_x, d_y);
+    if (op->has_ghost) {
+        rc = launch_tiles(op, L, 1, stream);
+        if (rc) return rc;
+    }
+    rc = launch_long(op, L, stream);
+    if (rc) return rc;
+    CU_TRY(cudaEventRecord(P->ev_tail, stream));
+    CU_TRY(cudaStreamWaitEvent(out, P->ev_tail, 0));
+    for (int k = 0; k < nb; ++k) {
+        if (!P->late[(size_t)k]) continue;
+        const i64 r0 = P->row_at[(size_t)k], r1 = P->row_at[(size_t)k + 1];
+        if (r1 > r0) CU_TRY(cudaMemcpyAsync((char*)h_y + (size_t)r0 * es, (const char*)d_y + (size_t)r0 * es, (size_t)(r1 - r0) * es, cudaMemcpyDeviceToHost, out));
+    }
+    CU_TRY(cudaEventRecord(P->ev_done, out));
+    CU_TRY(cudaStreamWaitEvent(stream, P->ev_done, 0));  // the caller's stream now orders after host y is complete
+    return HPCLA_OK;
 }
 
 extern "C" int hpcla_spmv_gather(hpcla_spmv* op, const void* d_x, void* stream_, void** d_gathered_out) {

@@ -22,7 +22,7 @@ struct TileShape {
     int rp_cap;         // row walk: staged row pointers per tile (multiple of 4)
     int general_elems;  // general kernel: products staged per tile
 };
-// avg_row: mean stored entries per row; irregular: general kernel only; overrides: 0 = none (tuning hooks)
+// avg_row: typical stored entries per row (the most common row length, else the mean); irregular: general kernel only; overrides: 0 = none (tuning hooks)
 TileShape tile_shape(int dtype, int itype, double avg_row, bool irregular, int lanes_override, int window_override);
 size_t rowwalk_smem_bytes(int dtype, int itype, const TileShape& shape);
 
@@ -34,7 +34,8 @@ struct SpmvLaunch {
     i64 nrows, nnz;
     TileShape shape;        // as fixed when the tile table was built
     const TileDesc* tiles;  // [ntiles+1]
-    const int* tile_list;   // nullptr: tiles 0..n_launch-1
+    const int* tile_list;   // nullptr: tiles tile_base .. tile_base + n_launch - 1
+    int tile_base = 0;
     int n_launch;
     // x addressing for a 1-based compressed column c:
     //   own  <=> own_lo <= c < own_lo + own_n           -> x_own[c - own_lo]   (x_own already offset to the first own source)
@@ -51,12 +52,16 @@ cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz
                                cudaStream_t st);
 // cls[t] = 0 (no rows), 1 (row-walk kernel), 2 (general kernel)
 cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int cap, int rp_cap, unsigned char* cls, cudaStream_t st);
+// hist[min(len, 1023)] += 1 for every row (hist: 1024 device counters, pre-zeroed)
+cudaError_t launch_row_len_hist(int itype, const void* rowptr, i64 nrows, unsigned long long* hist, cudaStream_t st);
 // rows longer than threshold: writes their local row ids (ascending not guaranteed) into rows_out (capacity cap), count via *count_out (device)
 cudaError_t launch_find_long_rows(int itype, const void* rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
                                   unsigned long long* count_out, cudaStream_t st);
 // flags[t] = 1 iff tile t references a column outside [own_lo, own_lo+own_n)
 cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n,
                                   unsigned char* flags, cudaStream_t st);
+// out[t] = largest own column of tile t, 0-based relative to own_lo, or -1
+cudaError_t launch_tile_maxcol(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n, i64* out, cudaStream_t st);
 cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 1
 cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 2
 

@@ -16,13 +16,23 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 
 #include "device.h"
 
+// A/B knobs of the row walk (alternate builds, tools/tune_spmv.py): predicated batches, gathers in flight per lane,
+// resident CTAs per SM the ComplexF64 instantiations are register-allocated for
+// (measured, profiles/r1e_tune_walk_variants.txt: predicated batches of 8 win on every stencil workload)
 #ifndef HPCLA_WALK_PRED
-#define HPCLA_WALK_PRED 0  // 1: predicated 4-wide batches in the row walk (A/B knob)
+#define HPCLA_WALK_PRED 1
+#endif
+#ifndef HPCLA_WALK_BATCH
+#define HPCLA_WALK_BATCH 8
+#endif
+#ifndef HPCLA_CPLX_CTAS
+#define HPCLA_CPLX_CTAS 3
 #endif
 
 namespace hpcla {
@@ -119,7 +129,7 @@ template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 
 constexpr int ROW_THREADS = 256;
 template <class T> struct RowCfg { static constexpr int CTAS = 8; };   // 32 registers per thread
 template <> struct RowCfg<double> { static constexpr int CTAS = 7; };  // 36
-template <> struct RowCfg<cplx> { static constexpr int CTAS = 5; };    // 48 (16-byte values)
+template <> struct RowCfg<cplx> { static constexpr int CTAS = HPCLA_CPLX_CTAS; };  // 48 (16-byte values)
 
 // x addressing: own columns are read straight from x.v (no local copy into `gathered`), ghosts from `gathered`.
 template <class T>
@@ -147,6 +157,7 @@ struct TileArgs {
     T* y;
     const TileDesc* tiles;
     const int* tile_list;
+    int tile_base;  // without a list: tiles tile_base, tile_base + 1, ...
     i64 nnz_total;
     i64 long_threshold;
     i64 safe_col;  // a column that is always valid to read (padding lanes)
@@ -181,7 +192,7 @@ __global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti
     T* prod = reinterpret_cast<T*>(smem_raw);
     constexpr int CHUNK = THREADS * GROUPS * 4;
     const int tid = threadIdx.x;
-    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
+    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : a.tile_base + (int)blockIdx.x;
     const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
     const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
     const i64 r0 = d0.x, r1 = d1.x;
@@ -326,25 +337,26 @@ __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const T
             const int b = (int)((i64)rp[r - rp_off] - 1 - s4);
             const int e = (int)((i64)rp[r - rp_off + 1] - 1 - s4);
             int k = b + lane;
+            constexpr int B = HPCLA_WALK_BATCH;
 #if HPCLA_WALK_PRED
-            for (; k < e; k += 4 * G) {  // 4 predicated gathers in flight per lane, then the adds in order
-                T p[4];
+            for (; k < e; k += B * G) {  // B predicated gathers in flight per lane, then the adds in order
+                T p[B];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < B; ++u) {
                     const int kk = k + u * G;
                     p[u] = (kk < e) ? el_mul(sval[kk], x_at<GHOST, T, Ti>(xv, scol[kk])) : el_zero(T());
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < B; ++u)
                     if (k + u * G < e) acc = el_add(acc, p[u]);
             }
 #else
-            for (; k + 3 * G < e; k += 4 * G) {  // 4 independent gathers in flight per lane, then the adds in order
-                T p[4];
+            for (; k + (B - 1) * G < e; k += B * G) {  // B independent gathers in flight per lane, then the adds in order
+                T p[B];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) p[u] = el_mul(sval[k + u * G], x_at<GHOST, T, Ti>(xv, scol[k + u * G]));
+                for (int u = 0; u < B; ++u) p[u] = el_mul(sval[k + u * G], x_at<GHOST, T, Ti>(xv, scol[k + u * G]));
 #pragma unroll
-                for (int u = 0; u < 4; ++u) acc = el_add(acc, p[u]);
+                for (int u = 0; u < B; ++u) acc = el_add(acc, p[u]);
             }
             for (; k < e; k += G) acc = el_add(acc, el_mul(sval[k], x_at<GHOST, T, Ti>(xv, scol[k])));
 #endif
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - (GHOST ? 1 : 0)
     Ti* scol = srp + rp_cap;
     T* sval = reinterpret_cast<T*>(scol + cap);
     const int tid = threadIdx.x;
-    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : (int)blockIdx.x;
+    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : a.tile_base + (int)blockIdx.x;
     const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
     const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
     const i64 r0 = d0.x, r1 = d1.x;
@@ -471,6 +483,21 @@ __global__ void build_tiles_kernel(const Ti* __restrict__ rowptr, i64 nrows, int
     tiles[k].nnz = (i64)rowptr[r] - 1;
 }
 
+// histogram of the row lengths (lengths >= 1023 share the last bin): the most common length sizes the tile window
+template <class Ti>
+__global__ void __launch_bounds__(256) row_len_hist_kernel(const Ti* __restrict__ rowptr, i64 nrows, unsigned long long* hist /* [1024] */) {
+    __shared__ unsigned int sh[1024];
+    for (int i = threadIdx.x; i < 1024; i += 256) sh[i] = 0;
+    __syncthreads();
+    for (i64 r = (i64)blockIdx.x * 256 + threadIdx.x; r < nrows; r += (i64)gridDim.x * 256) {
+        const i64 len = (i64)rowptr[r + 1] - (i64)rowptr[r];
+        atomicAdd(&sh[len < 1023 ? (int)len : 1023], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1024; i += 256)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
 template <class Ti>
 __global__ void find_long_rows_kernel(const Ti* __restrict__ rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
                                       unsigned long long* count) {
@@ -520,6 +547,32 @@ __global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ 
     const bool fits = (e - (s & ~(i64)3)) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap;
     const bool balanced = 2 * (e - s) >= (r1 - r0) * maxlen;
     if (lane == 0) cls[t] = (fits && balanced && e > s) ? 1 : 2;
+}
+
+// Largest own column (0-based, relative to the own segment) referenced by each tile, -1 if none: the prefix of x.v a
+// tile needs before it can run (staged host -> device pipeline, hpcla_spmv_run_staged).
+template <class Ti>
+__global__ void __launch_bounds__(256) tile_maxcol_kernel(const Ti* __restrict__ colval, const TileDesc* __restrict__ tiles, i64 own_lo,
+                                                          unsigned long long own_n, i64* __restrict__ out) {
+    __shared__ i64 sh[8];
+    const i64 t = blockIdx.x;
+    const i64 b = tiles[t].nnz, e = tiles[t + 1].nnz;
+    i64 m = -1;
+    for (i64 k = b + threadIdx.x; k < e; k += 256) {
+        const i64 c = (i64)colval[k] - own_lo;
+        if ((unsigned long long)c < own_n && c > m) m = c;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const i64 o = __shfl_xor_sync(0xffffffffu, m, d);
+        m = o > m ? o : m;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = sh[w] > m ? sh[w] : m;
+        out[t] = m;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -724,6 +777,14 @@ cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* til
     return cudaGetLastError();
 }
 
+cudaError_t launch_row_len_hist(int itype, const void* rowptr, i64 nrows, unsigned long long* hist, cudaStream_t st) {
+    if (nrows == 0) return cudaSuccess;
+    const int blocks = (int)std::min<i64>(148 * 8, (nrows + 255) / 256);
+    if (itype == HPCLA_I32) row_len_hist_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, nrows, hist);
+    else row_len_hist_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, nrows, hist);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_find_long_rows(int itype, const void* rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap, unsigned long long* count_out,
                                   cudaStream_t st) {
     if (nrows == 0) return cudaSuccess;
@@ -738,6 +799,13 @@ cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc*
     if (ntiles == 0) return cudaSuccess;
     if (itype == HPCLA_I32) classify_tiles_kernel<int><<<(unsigned)ntiles, 256, 0, st>>>((const int*)colval, tiles, own_lo, (unsigned long long)own_n, flags);
     else classify_tiles_kernel<long long><<<(unsigned)ntiles, 256, 0, st>>>((const long long*)colval, tiles, own_lo, (unsigned long long)own_n, flags);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_maxcol(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n, i64* out, cudaStream_t st) {
+    if (ntiles == 0) return cudaSuccess;
+    if (itype == HPCLA_I32) tile_maxcol_kernel<int><<<(unsigned)ntiles, 256, 0, st>>>((const int*)colval, tiles, own_lo, (unsigned long long)own_n, out);
+    else tile_maxcol_kernel<long long><<<(unsigned)ntiles, 256, 0, st>>>((const long long*)colval, tiles, own_lo, (unsigned long long)own_n, out);
     return cudaGetLastError();
 }
 
@@ -762,6 +830,7 @@ static TileArgs<T, Ti> tile_args(const SpmvLaunch& L) {
     a.y = (T*)L.y;
     a.tiles = L.tiles;
     a.tile_list = L.tile_list;
+    a.tile_base = L.tile_base;
     a.nnz_total = L.nnz;
     a.long_threshold = L.long_threshold;
     a.safe_col = L.own_n > 0 ? L.own_lo : 1;

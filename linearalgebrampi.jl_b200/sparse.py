@@ -408,6 +408,30 @@ def mul(y: HPCVector, A: HPCSparseMatrix, x: HPCVector) -> HPCVector:
     return y
 
 
+def mul_staged(y: HPCVector, A: HPCSparseMatrix, x: HPCVector, x_host, y_host) -> HPCVector:
+    """copyto!(x.v, x_host); mul!(y, A, x); copyto!(y_host, y.v) as ONE pipelined call (hpcla_spmv_run_staged).
+
+    This is the reference's CUDA path seen from the host — every `A * x` there stages x through the host and copies
+    the gathered vector back up (src/vectors.jl:423, 460), and mul! computes on host arrays (src/sparse.jl:2019-2037)
+    — with the upload, the multiply and the download overlapped block by block.  x_host / y_host: this rank's local
+    slices as (pinned) CPU torch tensors or numpy arrays of A's element type.  y_host is complete after the current
+    stream has been synchronised."""
+    _check_mul_args(A, x)
+    if y.local_size != A.nrows_local:
+        raise ValueError(f"DimensionMismatch: y holds {y.local_size} local rows, A has {A.nrows_local}")
+    if A.backend.ctx().world == "threads":
+        raise _lib.HPCLAError("mul_staged needs an NCCL world or a single rank")
+    for name, h, n in (("x_host", x_host, x.local_size), ("y_host", y_host, y.local_size)):
+        hn = h.numel() if hasattr(h, "numel") else h.size
+        if hn != n:
+            raise ValueError(f"DimensionMismatch: {name} holds {hn} elements, the local slice has {n}")
+        if hasattr(h, "is_cuda") and h.is_cuda:
+            raise ValueError(f"{name} must be a host array")
+    op = _bound_op(A, get_vector_plan(A, x), x)
+    _lib.check(_lib.lib().hpcla_spmv_run_staged(op, _lib.ptr(x_host), _lib.ptr(x.v), _lib.ptr(y.v), _lib.ptr(y_host), _current_stream(A.backend)))
+    return y
+
+
 def matvec(A: HPCSparseMatrix, x: HPCVector) -> HPCVector:
     """Base.:*(A, x) — src/sparse.jl:2096-2128.  Result partition = A.row_partition (hash cached in the plan)."""
     import torch

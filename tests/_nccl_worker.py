@@ -19,6 +19,7 @@ def relerr(y, ref):
 
 
 def main():
+    os.environ["HPCLA_STAGE_CHUNK_KB"] = "64"  # many small blocks at test size
     local_rank = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -38,6 +39,14 @@ def main():
         yT = la.transpose(A) * x
         g = la.execute_plan(la.get_vector_plan(A, x), A, x)
         torch.cuda.synchronize()
+        # staged multiply (host x in, host y out, pipelined): the halo waits for the last upload chunk
+        xh = torch.empty(x.local_size, dtype=x.v.dtype, pin_memory=True).copy_(x.v)
+        yh = torch.zeros(y.local_size, dtype=y.v.dtype, pin_memory=True)
+        x3, y3 = la.HPCVector.zeros(b, n), la.HPCVector.zeros(b, n)
+        for _ in range(2):
+            la.mul_staged(y3, A, x3, xh, yh)
+            torch.cuda.synchronize()
+            assert torch.equal(yh, y.v.cpu()) and torch.equal(y3.v, y.v), ("staged", kind)
         rp, c, v = S.stencil_local(kind, grid, 0, n, T, Ti)
         G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
         olocs = orc.distribute(G, P, itype="i32" if Ti == np.int32 else "i64")
