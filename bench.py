@@ -280,7 +280,7 @@ def run_b200_arm(args, spec):
     if op == "cg":
         bvec = la.matvec(A, la.HPCVector.from_local(np.ones(x.local_size, dtype=T), backend))  # b = A*1
 
-        def step():
+        def step():  # warm-up only; the timed region is ONE hpcla_cg call of `steps` iterations (a step = an iteration)
             la.cg(A, bvec, cg_iters_per_step)
     else:
         def step():
@@ -312,23 +312,18 @@ def run_b200_arm(args, spec):
     sampler.start()
     barrier()
     ev0.record()
-    for _ in range(steps):
-        step()
+    if op == "cg":
+        la.cg(A, bvec, steps)  # x0 = 0, r = p = b (one pass), then `steps` iterations, all scalars on the device
+    else:
+        for _ in range(steps):
+            step()
     ev1.record()
     barrier()
     sampler.stop()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = int(L.hpcla_spmv_launch_count(opnd)) - launches0
     region = "timed"
-    if len(sampler.samples) < 8:  # short timed region: keep the same kernel running so the clocks are seen under load
-        sampler.start()
-        t_end = time.time() + 0.4
-        while time.time() < t_end:
-            for _ in range(20):
-                step()
-            torch.cuda.synchronize()
-        sampler.stop()
-        region = "timed + 0.4 s probe of the same step"
+    n_samples = len(sampler.samples)
     if dist is not None:
         tmax = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -336,6 +331,21 @@ def run_b200_arm(args, spec):
         lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
         launches = int(lt.item())
+        ns = torch.tensor([n_samples], device="cuda", dtype=torch.int64)
+        dist.all_reduce(ns, op=dist.ReduceOp.MIN)
+        n_samples = int(ns.item())
+    if n_samples < 8 and op != "cg":
+        # short timed region: keep the same step running (the SAME number of steps on every rank: the multiply is
+        # collective) so that the clocks are sampled under load
+        probe_steps = int(min(4000, max(20, 400.0 / max(elapsed_ms / steps, 1e-3))))
+        sampler.start()
+        for i in range(probe_steps):
+            step()
+            if i % 20 == 19:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        sampler.stop()
+        region = f"timed + {probe_steps} more of the same step"
     ms_per_step = elapsed_ms / steps
     gflops = flops_step / (ms_per_step * 1e-3) / 1e9
     gbs = bytes_step / (ms_per_step * 1e-3) / 1e9

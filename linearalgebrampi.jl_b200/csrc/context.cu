@@ -194,7 +194,11 @@ extern "C" int hpcla_ctx_create(int device, int rank, int nranks, hpcla_ctx** ou
     c->device = device;
     c->rank = rank;
     c->nranks = nranks;
-    CU_TRY(cudaStreamCreateWithFlags(&c->halo_stream, cudaStreamNonBlocking));
+    // Highest priority: the small halo kernels (pack, NCCL send/recv) must get SMs ahead of the tens of thousands of
+    // pending CTAs of the interior multiply, or the exchange only starts when the multiply has drained.
+    int prio_least = 0, prio_greatest = 0;
+    CU_TRY(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CU_TRY(cudaStreamCreateWithPriority(&c->halo_stream, cudaStreamNonBlocking, prio_greatest));
     CU_TRY(cudaMalloc(&c->d_red_scratch, sizeof(double) * reduce_scratch_doubles()));
     CU_TRY(cudaMemset(c->d_red_scratch, 0, sizeof(double) * reduce_scratch_doubles()));
     CU_TRY(cudaMalloc(&c->d_red_out, sizeof(double) * 8));
@@ -779,6 +783,7 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     if (!op->x_in_place && op->own_n > 0) {  // local copy of src/vectors.jl:426-428, only when own columns have gaps
         CU_TRY(launch_local_copy(op->csr->dtype, d_x, op->d_local_src, op->d_local_dst, op->own_n, op->d_gathered, stream));
         op->launches += 1;
+        if (op->has_ghost) CU_TRY(cudaEventRecord(op->ev_x, stream));  // the boundary tiles (halo stream) read this copy
     }
     SpmvLaunch L;
     fill_launch(op, L, d_x, d_y);
@@ -801,21 +806,31 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
     int rc = set_device(op->ctx);
     if (rc) return rc;
     cudaStream_t stream = op->cur_stream;
-    if (op->has_peers) {
-        if (op->ctx->group) {
-            rc = exchange_finish_group(op);
-            if (rc) return rc;
-        }
+    cudaStream_t hs = op->ctx->halo_stream;
+    if (op->has_peers && op->ctx->group) {
+        rc = exchange_finish_group(op);
+        if (rc) return rc;
+    }
+    if (op->has_ghost) {
+        // Boundary tiles go on the (high-priority) halo stream, right behind the receives: they run next to the
+        // interior tiles instead of after them, so a step costs max(interior, halo + boundary), not their sum.
+        SpmvLaunch L;
+        fill_launch(op, L, op->cur_x, op->cur_y);
+        if (!op->x_in_place) CU_TRY(cudaStreamWaitEvent(hs, op->ev_x, 0));  // own columns come from the local copy
+        rc = launch_tiles(op, L, 1, hs);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(op->ev_halo, hs));
+        op->halo_recorded = true;
+    }
+    if (op->has_peers || op->has_ghost) {
         // x (contiguous sends) and the packed buffer are read on the halo stream: the caller's stream must not run
-        // ahead of them, and the boundary tiles need the ghosts
+        // ahead of them, nor ahead of the boundary rows of y
         CU_TRY(cudaStreamWaitEvent(stream, op->ev_halo, 0));
-        if (op->ctx->group) CU_TRY(cudaStreamWaitEvent(stream, op->ev_packed, 0));
+        if (op->ctx->group && op->has_peers) CU_TRY(cudaStreamWaitEvent(stream, op->ev_packed, 0));
     }
     if (op->has_ghost) {
         SpmvLaunch L;
         fill_launch(op, L, op->cur_x, op->cur_y);
-        rc = launch_tiles(op, L, 1, stream);
-        if (rc) return rc;
         rc = launch_long(op, L, stream);
         if (rc) return rc;
     }
@@ -1117,6 +1132,7 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     const bool multi = ctx->comm && ctx->nranks > 1;
     NcclApi* api = multi ? nccl_api() : nullptr;
     CU_TRY(launch_cg_init(dtype, n, d_b, d_x, r, p, ctx->d_red_scratch, d_s, stream));
+    op->launches += 1;
     if (multi) NCCL_TRY(api->AllReduce(d_s, d_s, 1, ncclFloat64, ncclSum, ctx->comm, stream));
     for (int k = 0; k < iters; ++k) {
         rc = hpcla_spmv_run(op, p, q, stream);
@@ -1126,6 +1142,7 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
         CU_TRY(launch_cg_update_xr(dtype, n, p, q, d_x, r, d_s + 2 * k, d_pq, ctx->d_red_scratch, d_s + 2 * (k + 1), stream));
         if (multi) NCCL_TRY(api->AllReduce(d_s + 2 * (k + 1), d_s + 2 * (k + 1), 1, ncclFloat64, ncclSum, ctx->comm, stream));
         CU_TRY(launch_cg_update_p(dtype, n, r, p, d_s + 2 * (k + 1), d_s + 2 * k, stream));
+        op->launches += 3;
     }
     std::vector<double> h((size_t)(2 * (iters + 1)));
     CU_TRY(cudaMemcpyAsync(h.data(), d_s, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream));

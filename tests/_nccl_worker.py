@@ -69,6 +69,8 @@ def main():
         m, n = 2000, 1500
         R = sp.random(m, n, density=0.01, random_state=np.random.default_rng(5), format="csr")
         R.data = np.random.default_rng(6).uniform(-1, 1, R.nnz)
+        R = (R @ sp.diags((np.arange(n) % 3 != 1).astype(np.float64))).tocsr()  # every third column empty: the send runs have holes
+        R.eliminate_zeros()
         R = R.astype(T)
         xh = np.random.default_rng(7).uniform(-1, 1, n).astype(T)
         xp = np.concatenate([[1], np.sort(np.random.default_rng(8).integers(1, n + 1, size=P - 1)) , [n + 1]]).astype(np.int64)
