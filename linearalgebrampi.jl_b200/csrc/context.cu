@@ -109,6 +109,7 @@ struct hpcla_csr {
     TileDesc* d_tiles = nullptr;
     i64 ntiles = 0;
     std::vector<unsigned char> tile_class;  // per tile: 0 no rows, 1 row-walk kernel, 2 general kernel
+    std::vector<TileDesc> h_tiles;          // host copy of the tile table [ntiles+1]
     i64 n_class[3] = {0, 0, 0};
     i64 long_threshold = 0, chunk_nnz = 0;
     i64 nlong = 0, nchunks = 0;
@@ -156,8 +157,9 @@ struct hpcla_spmv {
     void* d_sendbuf = nullptr;
     i64* d_send_idx = nullptr;                              // concatenated send_indices (all peers)
     i64 *d_local_src = nullptr, *d_local_dst = nullptr;     // only when needed (fallback / gather hook)
-    int* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
+    TileRec* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
     int n_list[2][2] = {{0, 0}, {0, 0}};
+    i64 list_tile0[2][2] = {{-1, -1}, {-1, -1}};  // first tile of a list of consecutive tiles, else -1
     std::vector<int> h_list[2][2];  // host copies (block boundaries of the staged multiply)
     struct HostPipe* pipe = nullptr;
     cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
@@ -352,9 +354,11 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         CU_TRY(launch_build_tiles(itype, d_rowptr, nrows, nnz, A->shape.window, A->d_tiles, A->ntiles, st));
         unsigned char* d_cls = nullptr;
         CU_TRY(cudaMalloc(&d_cls, (size_t)A->ntiles));
-        CU_TRY(launch_tile_class(itype, d_rowptr, A->d_tiles, A->ntiles, A->shape.cap, A->shape.rp_cap, d_cls, st));
+        CU_TRY(launch_tile_class(itype, d_rowptr, A->d_tiles, A->ntiles, A->shape.window, A->shape.cap, A->shape.rp_cap, d_cls, st));
         A->tile_class.assign((size_t)A->ntiles, 0);
+        A->h_tiles.resize((size_t)A->ntiles + 1);
         CU_TRY(cudaMemcpyAsync(A->tile_class.data(), d_cls, (size_t)A->ntiles, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(A->h_tiles.data(), A->d_tiles, sizeof(TileDesc) * ((size_t)A->ntiles + 1), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         cudaFree(d_cls);
         A->n_class[0] = A->n_class[1] = A->n_class[2] = 0;
@@ -522,9 +526,15 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
         for (int c = 0; c < 2; ++c)
             for (int g = 0; g < 2; ++g) {
                 op->n_list[c][g] = (int)lists[c][g].size();
-                if (lists[c][g].empty() || (i64)lists[c][g].size() == A->ntiles) continue;  // all tiles, in order: no list
-                CU_TRY(cudaMalloc(&op->d_list[c][g], sizeof(int) * lists[c][g].size()));
-                CU_TRY(cudaMemcpy(op->d_list[c][g], lists[c][g].data(), sizeof(int) * lists[c][g].size(), cudaMemcpyHostToDevice));
+                if (lists[c][g].empty()) continue;
+                if ((i64)lists[c][g].back() - (i64)lists[c][g].front() + 1 == (i64)lists[c][g].size()) op->list_tile0[c][g] = lists[c][g].front();
+                std::vector<TileRec> recs(lists[c][g].size());
+                for (size_t q = 0; q < recs.size(); ++q) {
+                    const TileDesc &t0 = A->h_tiles[(size_t)lists[c][g][q]], &t1 = A->h_tiles[(size_t)lists[c][g][q] + 1];
+                    recs[q] = TileRec{t0.row, t1.row, t0.nnz, t1.nnz};
+                }
+                CU_TRY(cudaMalloc(&op->d_list[c][g], sizeof(TileRec) * recs.size()));
+                CU_TRY(cudaMemcpy(op->d_list[c][g], recs.data(), sizeof(TileRec) * recs.size(), cudaMemcpyHostToDevice));
             }
     }
     op->seq = ctx->op_seq++;
@@ -679,7 +689,6 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
     L.nrows = A->nrows;
     L.nnz = A->nnz;
     L.shape = A->shape;
-    L.tiles = A->d_tiles;
     L.x_own = op->x_in_place ? (const void*)((const char*)d_x + (size_t)(op->own_src0 - 1) * es)
                              : (const void*)((const char*)op->d_gathered + (size_t)(op->own_lo - 1) * es);
     L.gathered = op->d_gathered;
@@ -695,8 +704,8 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
 static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t stream, const int* from = nullptr, const int* to = nullptr) {
     for (int c = 0; c < 2; ++c) {
         const int lo = from ? from[c] : 0, hi = to ? to[c] : op->n_list[c][which];
-        L.tile_list = op->d_list[c][which] ? op->d_list[c][which] + lo : nullptr;
-        L.tile_base = lo;  // without a list the list is the identity
+        L.recs = op->d_list[c][which] + lo;
+        L.tile0 = op->list_tile0[c][which] >= 0 ? op->list_tile0[c][which] + lo : -1;
         L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
         if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
@@ -870,8 +879,7 @@ static int build_pipe(hpcla_spmv* op) {
     if (!P->usable) return HPCLA_OK;
     P->nb = nb;
     // block boundaries in tiles, rows, and list positions
-    std::vector<TileDesc> tiles((size_t)A->ntiles + 1);
-    CU_TRY(cudaMemcpy(tiles.data(), A->d_tiles, sizeof(TileDesc) * tiles.size(), cudaMemcpyDeviceToHost));
+    const std::vector<TileDesc>& tiles = A->h_tiles;
     std::vector<i64> tb((size_t)nb + 1);
     P->row_at.resize((size_t)nb + 1);
     for (int k = 0; k <= nb; ++k) {

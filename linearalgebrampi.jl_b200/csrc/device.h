@@ -13,6 +13,11 @@ struct TileDesc {
     i64 nnz;
 };
 
+// What one CTA of a multiply kernel needs to know about its tile: rows [r0, r1), 0-based stored entries [s, e).
+struct TileRec {
+    i64 r0, r1, s, e;
+};
+
 // Tile shape of one matrix (see kernels.cu: shape_of).
 struct TileShape {
     int threads;        // CTA size of the row-walk kernel
@@ -33,9 +38,8 @@ struct SpmvLaunch {
     const void* nzval;
     i64 nrows, nnz;
     TileShape shape;        // as fixed when the tile table was built
-    const TileDesc* tiles;  // [ntiles+1]
-    const int* tile_list;   // nullptr: tiles tile_base .. tile_base + n_launch - 1
-    int tile_base = 0;
+    const TileRec* recs;    // [n_launch] the tiles of this launch, one CTA each
+    i64 tile0 = -1;         // >= 0: recs are the consecutive tiles tile0, tile0 + 1, ...
     int n_launch;
     // x addressing for a 1-based compressed column c:
     //   own  <=> own_lo <= c < own_lo + own_n           -> x_own[c - own_lo]   (x_own already offset to the first own source)
@@ -51,7 +55,8 @@ struct SpmvLaunch {
 cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles,
                                cudaStream_t st);
 // cls[t] = 0 (no rows), 1 (row-walk kernel), 2 (general kernel)
-cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int cap, int rp_cap, unsigned char* cls, cudaStream_t st);
+cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int window, int cap, int rp_cap, unsigned char* cls,
+                              cudaStream_t st);
 // hist[min(len, 1023)] += 1 for every row (hist: 1024 device counters, pre-zeroed)
 cudaError_t launch_row_len_hist(int itype, const void* rowptr, i64 nrows, unsigned long long* hist, cudaStream_t st);
 // rows longer than threshold: writes their local row ids (ascending not guaranteed) into rows_out (capacity cap), count via *count_out (device)

@@ -155,9 +155,9 @@ struct TileArgs {
     const T* nzval;
     XView<T> xv;
     T* y;
-    const TileDesc* tiles;
-    const int* tile_list;
-    int tile_base;  // without a list: tiles tile_base, tile_base + 1, ...
+    const TileRec* recs;  // one record per CTA of this launch
+    i64 tile0;            // >= 0: the launch covers the consecutive tiles tile0, tile0 + 1, ... (window arithmetic)
+    int window;           // stored entries per tile window
     i64 nnz_total;
     i64 long_threshold;
     i64 safe_col;  // a column that is always valid to read (padding lanes)
@@ -192,12 +192,12 @@ __global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti
     T* prod = reinterpret_cast<T*>(smem_raw);
     constexpr int CHUNK = THREADS * GROUPS * 4;
     const int tid = threadIdx.x;
-    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : a.tile_base + (int)blockIdx.x;
-    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
-    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
-    const i64 r0 = d0.x, r1 = d1.x;
+    // one 32-byte record per CTA: no list -> descriptor -> data chain of dependent loads in front of the first copy
+    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.recs + blockIdx.x));
+    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.recs + blockIdx.x) + 1);
+    const i64 r0 = d0.x, r1 = d0.y;
     if (r1 <= r0) return;
-    const i64 s = d0.y, e = d1.y;  // 0-based nonzero range of the tile
+    const i64 s = d1.x, e = d1.y;  // 0-based nonzero range of the tile
     const i64 s4 = s & ~(i64)3;    // 16-byte aligned start for every element width
     const i64 n = e - s4;
 
@@ -380,28 +380,48 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - (GHOST ? 1 : 0)
     Ti* scol = srp + rp_cap;
     T* sval = reinterpret_cast<T*>(scol + cap);
     const int tid = threadIdx.x;
-    const int tile = a.tile_list ? __ldg(a.tile_list + blockIdx.x) : a.tile_base + (int)blockIdx.x;
-    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile));
-    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.tiles + tile + 1));
-    const i64 r0 = d0.x, r1 = d1.x;
-    if (r1 <= r0) return;
-    const i64 s = d0.y, e = d1.y;  // 0-based nonzero range of the tile's rows
-    const i64 s4 = s & ~(i64)3;    // 16-byte aligned for every element width
-    const int n_st = (int)(e - s4);  // <= cap (classification)
+    // A launch over consecutive tiles knows where its window of the nonzero stream starts without reading anything:
+    // the bulk copies of the window are issued first, the tile record (rows, exact end) is fetched while they fly.
+    const bool contig = a.tile0 >= 0;
+    i64 w0 = 0;
+    int n_main = 0;
+    if (contig) {
+        w0 = (a.tile0 + (i64)blockIdx.x) * (i64)a.window;
+        const i64 left = (a.nnz_total - w0) & ~(i64)3;
+        n_main = (int)(left < (i64)a.window ? (left > 0 ? left : 0) : (i64)a.window);
+    }
+    uint64_t pol = 0;
+    if (tid == 0) {
+        mbar_init(bar, contig ? 2 : 1);
+        mbar_fence_init();
+        pol = l2_evict_first_policy();
+        if (contig) {
+            mbar_expect_tx(bar, (uint32_t)n_main * (uint32_t)(sizeof(Ti) + sizeof(T)));
+            if (n_main > 0) {
+                bulk_g2s(scol, a.colval + w0, (uint32_t)n_main * (uint32_t)sizeof(Ti), bar, pol);
+                bulk_g2s(sval, a.nzval + w0, (uint32_t)n_main * (uint32_t)sizeof(T), bar, pol);
+            }
+        }
+    }
+    // one 32-byte record per CTA (lists never hold tiles without rows)
+    const longlong2 d0 = __ldg(reinterpret_cast<const longlong2*>(a.recs + blockIdx.x));
+    const longlong2 d1 = __ldg(reinterpret_cast<const longlong2*>(a.recs + blockIdx.x) + 1);
+    const i64 r0 = d0.x, r1 = d0.y;
+    const i64 s = d1.x, e = d1.y;                // 0-based nonzero range of the tile's rows
+    const i64 s4 = contig ? w0 : (s & ~(i64)3);  // staged from here: 16-byte aligned for every element width
+    const int n_st = (int)(e - s4);              // <= cap (classification)
     const i64 avail = a.nnz_total - s4;
     const int n_bulk = (int)((((i64)n_st + 3) & ~(i64)3) <= avail ? (((i64)n_st + 3) & ~(i64)3) : (avail & ~(i64)3));
+    const int n_rest = n_bulk - n_main;  // >= 0: a window ends inside the tile's last row (or at the end of the matrix)
     const i64 rp0 = r0 & ~(i64)3;
     const int rp_need = (int)(r1 + 1 - rp0);  // entries rp0 .. r1, <= rp_cap (classification)
     const i64 rp_avail = rowptr_len - rp0;
     const int rp_bulk = (int)((((i64)rp_need + 3) & ~(i64)3) <= rp_avail ? (((i64)rp_need + 3) & ~(i64)3) : (rp_avail & ~(i64)3));
     if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        const uint64_t pol = l2_evict_first_policy();
-        mbar_expect_tx(bar, (uint32_t)n_bulk * (uint32_t)(sizeof(Ti) + sizeof(T)) + (uint32_t)rp_bulk * (uint32_t)sizeof(Ti));
-        if (n_bulk > 0) {
-            bulk_g2s(scol, a.colval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(Ti), bar, pol);
-            bulk_g2s(sval, a.nzval + s4, (uint32_t)n_bulk * (uint32_t)sizeof(T), bar, pol);
+        mbar_expect_tx(bar, (uint32_t)n_rest * (uint32_t)(sizeof(Ti) + sizeof(T)) + (uint32_t)rp_bulk * (uint32_t)sizeof(Ti));
+        if (n_rest > 0) {
+            bulk_g2s(scol + n_main, a.colval + s4 + n_main, (uint32_t)n_rest * (uint32_t)sizeof(Ti), bar, pol);
+            bulk_g2s(sval + n_main, a.nzval + s4 + n_main, (uint32_t)n_rest * (uint32_t)sizeof(T), bar, pol);
         }
         if (rp_bulk > 0) bulk_g2s(srp, a.rowptr + rp0, (uint32_t)rp_bulk * (uint32_t)sizeof(Ti), bar, pol);
     }
@@ -524,8 +544,8 @@ __global__ void __launch_bounds__(256) classify_tiles_kernel(const Ti* __restric
 // completely staged within `cap` nonzeros and `rp_cap` row pointers, and mean row length >= half the longest, i.e. the
 // lanes of the walk are well used), 2 = general kernel.
 template <class Ti>
-__global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ rowptr, const TileDesc* __restrict__ tiles, i64 ntiles, int cap, int rp_cap,
-                                                         unsigned char* cls) {
+__global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ rowptr, const TileDesc* __restrict__ tiles, i64 ntiles, int window, int cap,
+                                                         int rp_cap, unsigned char* cls) {
     const i64 t = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= ntiles) return;
@@ -544,7 +564,7 @@ __global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ 
         const i64 o = __shfl_xor_sync(0xffffffffu, maxlen, m);
         maxlen = o > maxlen ? o : maxlen;
     }
-    const bool fits = (e - (s & ~(i64)3)) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap;
+    const bool fits = (e - t * (i64)window) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap;  // staged from the window start
     const bool balanced = 2 * (e - s) >= (r1 - r0) * maxlen;
     if (lane == 0) cls[t] = (fits && balanced && e > s) ? 1 : 2;
 }
@@ -769,11 +789,12 @@ cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int cap, int rp_cap, unsigned char* cls, cudaStream_t st) {
+cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int window, int cap, int rp_cap, unsigned char* cls,
+                              cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
     const int blocks = blocks_for(ntiles, 8);
-    if (itype == HPCLA_I32) tile_class_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, tiles, ntiles, cap, rp_cap, cls);
-    else tile_class_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, tiles, ntiles, cap, rp_cap, cls);
+    if (itype == HPCLA_I32) tile_class_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, tiles, ntiles, window, cap, rp_cap, cls);
+    else tile_class_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, tiles, ntiles, window, cap, rp_cap, cls);
     return cudaGetLastError();
 }
 
@@ -828,9 +849,9 @@ static TileArgs<T, Ti> tile_args(const SpmvLaunch& L) {
     a.nzval = (const T*)L.nzval;
     a.xv = make_xview<T>(L.x_own, L.gathered, L.own_lo, L.own_n);
     a.y = (T*)L.y;
-    a.tiles = L.tiles;
-    a.tile_list = L.tile_list;
-    a.tile_base = L.tile_base;
+    a.recs = L.recs;
+    a.tile0 = L.tile0;
+    a.window = L.shape.window;
     a.nnz_total = L.nnz;
     a.long_threshold = L.long_threshold;
     a.safe_col = L.own_n > 0 ? L.own_lo : 1;

@@ -98,6 +98,7 @@ def main():
         configs.append({"HPCLA_LANES": int(g), "HPCLA_TILE_WINDOW": int(w)})
     for w in [int(v) for v in args.windows.split(",") if v]:
         configs.append({"HPCLA_TILE_WINDOW": w})
+
     ref = None
     for env in configs:
         ms, info, res = time_config(A, x, y, env, args.reps)
