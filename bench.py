@@ -399,7 +399,15 @@ def run_b200_arm(args, spec):
 
     peak, peak_src = measured_peak()
     per_gpu_gbs = gbs / world
-    roofline = {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": None,
+    traffic = None  # ncu DRAM bytes per launch of the dominant kernel (one --set full capture, profiles/traffic.json)
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            entry = json.load(f).get(args.workload)
+        if entry and world == 1:
+            traffic = int(entry["bytes"])
+    except Exception:
+        traffic = None
+    roofline = {"bound": "hbm", "achieved": per_gpu_gbs, "peak": peak, "unit": "GB/s", "frac": per_gpu_gbs / peak, "traffic": traffic,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": per_gpu_gbs / NOMINAL_HBM_GBS,
                 "kernel": ("spmv_rowwalk_kernel" if info["rowwalk_tiles"] >= info["general_tiles"] else "spmv_tile_kernel") + ("" if world == 1 else " (interior + boundary launches; step time includes the NCCL halo)"),
                 "algorithmic_bytes_per_step": bytes_step, "flops_per_step": flops_step}
