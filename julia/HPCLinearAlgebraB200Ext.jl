@@ -131,6 +131,21 @@ function LinearAlgebra.mul!(y::HPCVector{T,B}, A::HPCSparseMatrix{T,Ti,B}, x::HP
     return y
 end
 
+# --- staged multiply for host-resident vectors: x_host -> x.v, y.v = A*x, y.v -> y_host, pipelined over row blocks -----
+#     (what every A*x of the reference's CUDA path does with two full PCIe copies, src/vectors.jl:423, 460).
+#     x_host / y_host: this rank's local slices; pin them (CUDA.pin) for asynchronous copies.  y_host is complete
+#     after CUDA.synchronize() of the task-local stream.
+function mul_staged!(y_host::Vector{T}, y::HPCVector{T,B}, A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T,B}, x_host::Vector{T}) where {T,Ti,B<:CuB}
+    length(x_host) == length(x.v) && length(y_host) == length(y.v) || throw(DimensionMismatch("host slices must match the local slices"))
+    plan = get_vector_plan(A, x)
+    b = _bind(A, x, plan)
+    GC.@preserve x y x_host y_host begin
+        _check(@ccall(libhpcla.hpcla_spmv_run_staged(b.op::Ptr{Cvoid}, pointer(x_host)::Ptr{Cvoid}, _dptr(x.v)::Ptr{Cvoid}, _dptr(y.v)::Ptr{Cvoid},
+                  pointer(y_host)::Ptr{Cvoid}, _stream()::Ptr{Cvoid})::Cint), "hpcla_spmv_run_staged")
+    end
+    return y_host
+end
+
 # --- transpose(A) * x: src/sparse.jl:2375-2379 already materialises and caches A^T and calls A_transposed * x, which
 #     now dispatches to the method above; nothing to override.  (The one-time TransposePlan stays the reference's.)
 
