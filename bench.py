@@ -62,6 +62,10 @@ def workload_spec(name: str, n_gpus: int) -> dict:
         return dict(name="powerlaw 20M x 20M Float32 Int32", kind=3, grid=(20_000_000, 1, 1), T="f32", Ti="i32", op="mul", scaling="strong")
     if name == "powerlaw-2m":
         return dict(name="powerlaw 2M x 2M Float32 Int32", kind=3, grid=(2_000_000, 1, 1), T="f32", Ti="i32", op="mul", scaling="strong")
+    if name.startswith("poisson256-spmm"):  # A * B::HPCMatrix with k columns, e.g. poisson256-spmm8
+        k = int(name[len("poisson256-spmm"):] or 8)
+        g = weak_grid(n_gpus)
+        return dict(name=f"poisson3d_7pt {g[0]}x{g[1]}x{g[2]} times a dense {k}-column HPCMatrix", kind=1, grid=g, T="f64", Ti="i32", op="spmm", scaling="weak", ncols=k)
     if name == "cg-512":
         g = (512, 512, 512) if n_gpus == 8 else weak_grid(n_gpus)
         return dict(name=f"CG on poisson3d_7pt {g[0]}x{g[1]}x{g[2]}", kind=1, grid=g, T="f64", Ti="i32", op="cg", scaling="weak")
@@ -81,6 +85,12 @@ def algorithmic_bytes_flops(n_rows, n_cols, nnz, T, Ti, op):
         b += 12 * n_rows * sT
         f += 10 * n_rows
     return b, f
+
+
+def spmm_bytes_flops(n_rows, n_cols, nnz, T, Ti, k):
+    """A read once, k columns of B read and k columns of C written."""
+    sT, sI = np.dtype(NP_T[T]).itemsize, np.dtype(NP_TI[Ti]).itemsize
+    return nnz * (sT + sI) + (n_rows + 1) * sI + k * (n_cols + n_rows) * sT, (8 if T == "c128" else 2) * nnz * k
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -267,6 +277,8 @@ def run_b200_arm(args, spec):
     nnz_local = Aop.nnz_local
     nnz = int(la.comm_allreduce(backend.comm, nnz_local, "+"))
     bytes_step, flops_step = algorithmic_bytes_flops(n, n, nnz, spec["T"], spec["Ti"], op)
+    if op == "spmm":
+        bytes_step, flops_step = spmm_bytes_flops(n, n, nnz, spec["T"], spec["Ti"], spec["ncols"])
     plan = la.get_vector_plan(Aop, x)
     L = la._lib.lib()
     opnd = la.sparse._bound_op(Aop, plan, x)
@@ -282,6 +294,17 @@ def run_b200_arm(args, spec):
 
         def step():  # warm-up only; the timed region is ONE hpcla_cg call of `steps` iterations (a step = an iteration)
             la.cg(A, bvec, cg_iters_per_step)
+    elif op == "spmm":
+        k = spec["ncols"]
+        Bm = la.HPCMatrix.from_local(torch.stack([la.synth.vector(n, backend, seed=la.synth.X_SEED + j).v for j in range(k)]).T, backend)
+        cols_ref = (A * Bm.column(k - 1)).v.clone()
+
+        def step():
+            step.C = la.spmm(A, Bm)
+
+        step()
+        if not torch.equal(step.C.A[:, k - 1], cols_ref):
+            raise SystemExit("bench.py: A*B disagrees with A*B[:, k]; refusing to time a wrong result")
     else:
         def step():
             la.mul(y, Aop, x)
@@ -352,7 +375,7 @@ def run_b200_arm(args, spec):
 
     # ---- end to end: host (pinned) x in, host y out, every step ---------------------------------------------------
     e2e = None
-    if op != "cg":
+    if op not in ("cg", "spmm"):
         xh = torch.empty(x.local_size, dtype=x.v.dtype, pin_memory=True).copy_(x.v)
         yh = torch.empty(y.local_size, dtype=y.v.dtype, pin_memory=True)
 

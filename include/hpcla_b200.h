@@ -150,6 +150,16 @@ int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x, void* d_y,
 /* Single-process world: call begin on every rank, then finish on every rank. */
 int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
 int hpcla_spmv_finish(hpcla_spmv* op);
+/* C = A * B for a dense right-hand side — replaces Base.:*(A::HPCSparseMatrix, B::HPCMatrix) (src/sparse.jl:2391-2413:
+ * a loop of ncols `A * B[:, k]` with a column extraction and a ghost exchange each) by one halo exchange for all
+ * columns and kernels that stage every tile of A once per 4 columns.  d_B: B.A, this rank's rows of B, column-major
+ * with leading dimension ldb (x.v of column k = d_B + k*ldb, partitioned like the plan's x); d_C: the local block of
+ * the result (rows of A.row_partition), column-major, ldc.  Same calling discipline as hpcla_spmv_run / begin+finish.
+ * Fails with HPCLA_ERR_STATE when A's own columns are not a contiguous run of B's local rows (the caller then
+ * multiplies column by column, like the reference). */
+int hpcla_spmm_run(hpcla_spmv* op, const void* d_B, int64_t ldb, void* d_C, int64_t ldc, int ncols, void* stream);
+int hpcla_spmm_begin(hpcla_spmv* op, const void* d_B, int64_t ldb, void* d_C, int64_t ldc, int ncols, void* stream);
+int hpcla_spmm_finish(hpcla_spmv* op);
 /* Parity hook: fills plan.gathered exactly as execute_plan! would and returns its device address
  * (gathered[d] == x_global[col_indices[d]]).  Same calling discipline as run (NCCL) / begin+finish (group: this is
  * the begin half; hpcla_spmv_gather_finish the other). */
@@ -175,6 +185,22 @@ int hpcla_nrm2(hpcla_ctx* ctx, int dtype, int64_t n, const void* d_x, void* resu
 /* y .= alpha .* x .+ beta .* y — the fused broadcast of src/vectors.jl:1203-1221; alpha, beta: T on the host. */
 int hpcla_axpby(hpcla_ctx* ctx, int dtype, int64_t n, const void* alpha, const void* d_x, const void* beta, void* d_y,
                 void* stream);
+/* VectorRepartitionPlan(x, p) — src/vectors.jl:519-616 — as a pure function of the two partitions (1-based starts,
+ * nranks+1 entries each).  Outputs (capacity nranks each): send_rank_ids / send_first (1-based first local index of the
+ * range in x.v, = first(send_ranges[i])) / send_count; recv_rank_ids / recv_count / recv_offset (1-based position in
+ * the result, = recv_offsets[i]); local3 = {first(local_src_range), length(local_src_range), local_dst_offset};
+ * result_local_size.  Same field values as the reference's plan, ranks ascending. */
+int hpcla_repartition_plan(int rank, int nranks, const int64_t* old_partition, const int64_t* new_partition,
+                           int64_t* n_send_out, int64_t* send_rank_ids, int64_t* send_first, int64_t* send_count,
+                           int64_t* n_recv_out, int64_t* recv_rank_ids, int64_t* recv_count, int64_t* recv_offset,
+                           int64_t* local3_out, int64_t* result_local_size_out);
+/* execute_plan!(plan::VectorRepartitionPlan, x) — src/vectors.jl:624-676 (host-staged Isend/Irecv, tag 92) — on the
+ * device: one device-to-device copy for the local overlap, grouped ncclSend/ncclRecv of contiguous ranges for the
+ * rest, straight between x.v (d_src) and the result (d_dst, result_local_size elements).  Collective; enqueue only. */
+int hpcla_repartition_run(hpcla_ctx* ctx, int dtype, int64_t n_send, const int64_t* send_rank_ids,
+                          const int64_t* send_first, const int64_t* send_count, int64_t n_recv,
+                          const int64_t* recv_rank_ids, const int64_t* recv_count, const int64_t* recv_offset,
+                          const int64_t* local3, const void* d_src, void* d_dst, void* stream);
 /* Fixed-iteration conjugate gradients composed from the operations above (the reference ships no CG):
  * x0 = 0, r = b, p = r; iters times { q = A p; alpha = rr/dot(p,q); x += alpha p; r -= alpha q; rr' = dot(r,r);
  * p = r + (rr'/rr) p }.  All scalars stay on the device; no host synchronisation inside the loop.  F32/F64 only.

@@ -12,13 +12,17 @@ from .backends import (  # noqa: F401
     backend_cuda_mpi, backend_cuda_serial, backends_compatible, backends_threads, comm_allgather, comm_allreduce,
     comm_barrier, comm_bcast, comm_exchange, comm_rank, comm_size, eltype_backend, indextype_backend, retype_backend,
 )
-from .vectors import HPCVector, axpby, compute_partition_hash, dot, norm, uniform_partition  # noqa: F401
+from .vectors import (  # noqa: F401
+    HPCVector, VectorRepartitionPlan, axpby, compute_partition_hash, dot, get_repartition_plan, norm, repartition, uniform_partition,
+)
 from .sparse import (  # noqa: F401
     HPCSparseMatrix, Transpose, VectorPlan, build_vector_plan, cache_sizes, cg, clear_plan_cache, compute_structural_hash,
     execute_plan, get_vector_plan, materialize_transpose, matvec, mul, mul_staged, spmv_info, to_backend, transpose, transpose_matvec,
     vec_adjoint_mul, vec_transpose_mul,
 )
-from . import sparse, synth, vectors, backends  # noqa: F401
+from .dense import HPCMatrix, spmm  # noqa: F401
+from . import sparse, synth, vectors, backends, dense  # noqa: F401
 
 HPCVector_local = HPCVector.from_local
+HPCMatrix_local = HPCMatrix.from_local
 HPCSparseMatrix_local = HPCSparseMatrix.from_local

@@ -79,6 +79,9 @@ SIGNATURES = {
     "hpcla_spmv_run_staged": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_spmv_begin": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_finish": (_i, [_vp]),
+    "hpcla_spmm_run": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "hpcla_spmm_begin": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),
+    "hpcla_spmm_finish": (_i, [_vp]),
     "hpcla_spmv_gather": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_gather_finish": (_i, [_vp]),
     "hpcla_spmv_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -88,6 +91,8 @@ SIGNATURES = {
     "hpcla_nrm2": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "hpcla_axpby": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_cg": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "hpcla_repartition_plan": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hpcla_repartition_run": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     # include/hpcla_synth.h
     "hpcla_synth_stencil_rows": (_i64, [_i, _i64, _i64, _i64]),
     "hpcla_synth_stencil_nnz": (_i64, [_i, _i64, _i64, _i64, _i64, _i64]),

@@ -169,6 +169,13 @@ struct hpcla_spmv {
     void* cur_y = nullptr;
     cudaStream_t cur_stream = nullptr;
     int phase = 0;  // 0 idle, 1 multiply begun, 2 gather begun
+    // sparse x dense: compact row-major ghost rows / packed send rows for up to mm_cols columns
+    void *d_ghost_rm = nullptr, *d_sendbuf_rm = nullptr;
+    int mm_cols = 0;
+    const void* mm_B = nullptr;
+    void* mm_C = nullptr;
+    i64 mm_ldb = 0, mm_ldc = 0;
+    int mm_ncols = 0;
     const void* persist_x = nullptr;  // x.v currently covered by the L2 persisting window (HPCLA_X_PERSIST)
     cudaStream_t persist_stream = nullptr;
     std::atomic<long long> epoch{0};  // exchanges begun (a peer's finish checks that I have begun the matching one)
@@ -568,6 +575,8 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
         if ((i64)g->ops.size() > op->seq) g->ops[(size_t)op->seq][(size_t)op->ctx->rank] = nullptr;
     }
     cudaFree(op->d_gathered);
+    cudaFree(op->d_ghost_rm);
+    cudaFree(op->d_sendbuf_rm);
     cudaFree(op->d_sendbuf);
     cudaFree(op->d_send_idx);
     cudaFree(op->d_local_src);
@@ -856,6 +865,155 @@ extern "C" int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// sparse x dense: C = A * B, B and C column-major local blocks (HPCMatrix.A), all columns share one halo exchange
+// ---------------------------------------------------------------------------------------------------------------
+static i64 ghost_number(const hpcla_spmv* op, i64 pos1 /* 1-based position in gathered */) {
+    return pos1 < op->own_lo ? pos1 - 1 : pos1 - 1 - op->own_n;
+}
+
+static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream) {
+    const hpcla_csr* A = op->csr;
+    const size_t es = dtype_size(A->dtype);
+    SpmmLaunch L;
+    L.dtype = A->dtype;
+    L.itype = A->itype;
+    L.rowptr = A->d_rowptr;
+    L.colval = A->d_colval;
+    L.nzval = A->d_nzval;
+    L.nrows = A->nrows;
+    L.nnz = A->nnz;
+    L.shape = A->shape;
+    L.b_own = (const char*)op->mm_B + (size_t)(op->own_src0 - 1) * es;
+    L.ldb = op->mm_ldb;
+    L.ghost = op->d_ghost_rm;
+    L.ncols = op->mm_ncols;
+    L.own_lo = op->own_lo;
+    L.own_n = op->own_n;
+    L.has_ghost = ghost;
+    L.c = op->mm_C;
+    L.ldc = op->mm_ldc;
+    const bool walk = spmm_supports_rowwalk(A->shape);
+    for (int k0 = 0; k0 < op->mm_ncols;) {
+        L.k0 = k0;
+        L.kn = op->mm_ncols - k0 >= 4 ? 4 : 1;
+        for (int c = 0; c < 2; ++c) {
+            L.recs = op->d_list[c][which];
+            L.tile0 = op->list_tile0[c][which];
+            L.n_launch = op->n_list[c][which];
+            if (L.n_launch <= 0) continue;
+            if (c == 0 && walk) CU_TRY(launch_spmm_rowwalk(L, stream));
+            else CU_TRY(launch_spmm_rows(L, stream));
+            op->launches += 1;
+        }
+        k0 += L.kn;
+    }
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmm_begin(hpcla_spmv* op, const void* d_B, int64_t ldb, void* d_C, int64_t ldc, int ncols, void* stream_) {
+    if (!op || ncols < 0 || (op->n_x_local > 0 && ncols > 0 && !d_B) || (op->csr->nrows > 0 && ncols > 0 && !d_C)) return fail(HPCLA_ERR_ARG, "hpcla_spmm_begin: bad arguments");
+    if (ldb < op->n_x_local || ldc < op->csr->nrows) return fail(HPCLA_ERR_ARG, "hpcla_spmm_begin: leading dimensions smaller than the local blocks");
+    if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmm_begin: the previous call was not finished");
+    if (!op->x_in_place) return fail(HPCLA_ERR_STATE, "hpcla_spmm_begin: the own columns of A are not a contiguous run of B's local rows; multiply column by column");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    hpcla_ctx* ctx = op->ctx;
+    cudaStream_t stream = (cudaStream_t)stream_, hs = ctx->halo_stream;
+    const int dtype = op->csr->dtype;
+    const size_t es = dtype_size(dtype);
+    op->mm_B = d_B;
+    op->mm_C = d_C;
+    op->mm_ldb = ldb;
+    op->mm_ldc = ldc;
+    op->mm_ncols = ncols;
+    op->cur_stream = stream;
+    op->phase = 3;
+    if (ncols == 0) return HPCLA_OK;
+    const i64 n_ghost = op->plan.n_gathered - op->own_n;
+    if (op->has_peers && ncols > op->mm_cols) {  // (re)size the exchange buffers
+        CU_TRY(cudaDeviceSynchronize());
+        cudaFree(op->d_ghost_rm);
+        cudaFree(op->d_sendbuf_rm);
+        op->d_ghost_rm = op->d_sendbuf_rm = nullptr;
+        CU_TRY(cudaMalloc(&op->d_ghost_rm, es * (size_t)std::max<i64>(n_ghost, 1) * (size_t)ncols));
+        CU_TRY(cudaMalloc(&op->d_sendbuf_rm, es * (size_t)std::max<i64>(op->total_send, 1) * (size_t)ncols));
+        op->mm_cols = ncols;
+    }
+    if (op->has_peers) {
+        CU_TRY(cudaEventRecord(op->ev_x, stream));
+        CU_TRY(cudaStreamWaitEvent(hs, op->ev_x, 0));
+        const bool group = ctx->group != nullptr;
+        if (group)  // my packed rows may still be read by a peer's copy of the previous product
+            for (const Seg& sg : op->sends) {
+                hpcla_spmv* peer = group_peer(op, sg.peer);
+                if (peer && peer->halo_recorded) CU_TRY(cudaStreamWaitEvent(hs, peer->ev_halo, 0));
+            }
+        if (op->total_send > 0) {
+            CU_TRY(launch_pack_rows(dtype, d_B, ldb, op->d_send_idx, op->total_send, ncols, op->d_sendbuf_rm, hs));
+            op->launches += 1;
+        }
+        CU_TRY(cudaEventRecord(op->ev_packed, hs));
+        op->epoch.fetch_add(1, std::memory_order_release);
+        if (!group && ctx->comm) {
+            NcclApi* api = nccl_api();
+            size_t per = 1;
+            const ncclDataType_t nt = nccl_type(dtype, &per);
+            NCCL_TRY(api->GroupStart());
+            for (const Seg& sg : op->sends)  // one message per peer: its rows, all columns adjacent
+                NCCL_TRY(api->Send((const char*)op->d_sendbuf_rm + (size_t)sg.start * ncols * es, (size_t)sg.count * ncols * per, nt, sg.peer, ctx->comm, hs));
+            for (const Seg& r : op->recvs)
+                NCCL_TRY(api->Recv((char*)op->d_ghost_rm + (size_t)ghost_number(op, r.start) * ncols * es, (size_t)r.count * ncols * per, nt, r.peer, ctx->comm, hs));
+            NCCL_TRY(api->GroupEnd());
+        }
+    }
+    return spmm_tiles(op, 0, false, stream);  // interior tiles while the halo is in flight
+}
+
+extern "C" int hpcla_spmm_finish(hpcla_spmv* op) {
+    if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmm_finish: null");
+    if (op->phase != 3) return fail(HPCLA_ERR_STATE, "hpcla_spmm_finish: no product in flight");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    hpcla_ctx* ctx = op->ctx;
+    cudaStream_t stream = op->cur_stream, hs = ctx->halo_stream;
+    const size_t es = dtype_size(op->csr->dtype);
+    const int ncols = op->mm_ncols;
+    op->phase = 0;
+    if (ncols == 0 || !op->has_peers) return HPCLA_OK;
+    if (ctx->group) {  // single-process world: copy each peer's packed rows into my ghost rows
+        for (const Seg& r : op->recvs) {
+            hpcla_spmv* peer = group_peer(op, r.peer);
+            if (!peer || peer->epoch.load(std::memory_order_acquire) < op->epoch.load(std::memory_order_acquire) || peer->mm_ncols != ncols)
+                return fail(HPCLA_ERR_STATE, "hpcla_spmm_finish: rank %d has not begun the matching product", r.peer);
+            const Seg* ps = nullptr;
+            for (const Seg& sg : peer->sends)
+                if (sg.peer == ctx->rank) ps = &sg;
+            if (!ps || ps->count != r.count) return fail(HPCLA_ERR_STATE, "hpcla_spmm_finish: rank %d and rank %d disagree on the halo size", r.peer, ctx->rank);
+            CU_TRY(cudaStreamWaitEvent(hs, peer->ev_packed, 0));
+            CU_TRY(cudaMemcpyAsync((char*)op->d_ghost_rm + (size_t)ghost_number(op, r.start) * ncols * es, (const char*)peer->d_sendbuf_rm + (size_t)ps->start * ncols * es,
+                                   (size_t)r.count * ncols * es, cudaMemcpyDefault, hs));
+        }
+    }
+    if (op->has_ghost) {  // boundary tiles behind the receives, on the halo stream
+        rc = spmm_tiles(op, 1, true, hs);
+        if (rc) return rc;
+    }
+    CU_TRY(cudaEventRecord(op->ev_halo, hs));
+    op->halo_recorded = true;
+    CU_TRY(cudaStreamWaitEvent(stream, op->ev_halo, 0));
+    if (ctx->group) CU_TRY(cudaStreamWaitEvent(stream, op->ev_packed, 0));
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmm_run(hpcla_spmv* op, const void* d_B, int64_t ldb, void* d_C, int64_t ldc, int ncols, void* stream) {
+    if (op && op->ctx->group && op->ctx->nranks > 1 && op->has_peers)
+        return fail(HPCLA_ERR_STATE, "hpcla_spmm_run: in a single-process world call hpcla_spmm_begin on every rank, then hpcla_spmm_finish");
+    int rc = hpcla_spmm_begin(op, d_B, ldb, d_C, ldc, ncols, stream);
+    if (rc) return rc;
+    return hpcla_spmm_finish(op);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // staged multiply: host x -> x.v, y.v = A * x, y.v -> host y, pipelined over row blocks
 // ---------------------------------------------------------------------------------------------------------------
 static int build_pipe(hpcla_spmv* op) {
@@ -1116,6 +1274,34 @@ extern "C" int hpcla_axpby(hpcla_ctx* ctx, int dtype, int64_t n, const void* alp
     int rc = set_device(ctx);
     if (rc) return rc;
     CU_TRY(launch_axpby(dtype, n, alpha, d_x, beta, d_y, (cudaStream_t)stream));
+    return HPCLA_OK;
+}
+
+// execute_plan!(plan::VectorRepartitionPlan, x) — src/vectors.jl:624-676 — on the device: the local overlap is one
+// device-to-device copy, every other overlap one ncclSend / ncclRecv of a contiguous range straight between x.v and the
+// result (the reference stages the whole vector through the host and packs per-peer buffers, tag 92).
+extern "C" int hpcla_repartition_run(hpcla_ctx* ctx, int dtype, int64_t n_send, const int64_t* send_rank_ids, const int64_t* send_first,
+                                     const int64_t* send_count, int64_t n_recv, const int64_t* recv_rank_ids, const int64_t* recv_count,
+                                     const int64_t* recv_offset, const int64_t* local3, const void* d_src, void* d_dst, void* stream_) {
+    if (!ctx || !dtype_size(dtype) || n_send < 0 || n_recv < 0 || !local3) return fail(HPCLA_ERR_ARG, "hpcla_repartition_run: bad arguments");
+    if ((n_send > 0 || n_recv > 0) && !ctx->comm) return fail(HPCLA_ERR_STATE, "hpcla_repartition_run: the plan exchanges data but the context has no NCCL communicator");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t es = dtype_size(dtype);
+    if (local3[1] > 0)
+        CU_TRY(cudaMemcpyAsync((char*)d_dst + (size_t)(local3[2] - 1) * es, (const char*)d_src + (size_t)(local3[0] - 1) * es, (size_t)local3[1] * es, cudaMemcpyDeviceToDevice, stream));
+    if (n_send > 0 || n_recv > 0) {
+        NcclApi* api = nccl_api();
+        size_t per = 1;
+        const ncclDataType_t nt = nccl_type(dtype, &per);
+        NCCL_TRY(api->GroupStart());
+        for (i64 i = 0; i < n_send; ++i)
+            NCCL_TRY(api->Send((const char*)d_src + (size_t)(send_first[i] - 1) * es, (size_t)send_count[i] * per, nt, (int)send_rank_ids[i], ctx->comm, stream));
+        for (i64 i = 0; i < n_recv; ++i)
+            NCCL_TRY(api->Recv((char*)d_dst + (size_t)(recv_offset[i] - 1) * es, (size_t)recv_count[i] * per, nt, (int)recv_rank_ids[i], ctx->comm, stream));
+        NCCL_TRY(api->GroupEnd());
+    }
     return HPCLA_OK;
 }
 

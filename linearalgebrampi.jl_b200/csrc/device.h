@@ -70,6 +70,33 @@ cudaError_t launch_tile_maxcol(int itype, const void* colval, const TileDesc* ti
 cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 1
 cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 2
 
+// Sparse x dense: kn (1 or 4) columns k0 .. k0+kn of C = A * B over the tiles of `recs`.
+struct SpmmLaunch {
+    int dtype, itype;
+    const void* rowptr;
+    const void* colval;
+    const void* nzval;
+    i64 nrows, nnz;
+    TileShape shape;
+    const TileRec* recs;
+    i64 tile0 = -1;
+    int n_launch;
+    const void* b_own;  // B's local block, column-major, at the first own source row (column 0)
+    i64 ldb;
+    const void* ghost;  // compact row-major ghost rows: ghost[g * ncols + k]
+    int ncols;
+    i64 own_lo, own_n;
+    bool has_ghost;
+    void* c;  // C's local block, column-major
+    i64 ldc;
+    int k0, kn;
+};
+bool spmm_supports_rowwalk(const TileShape& shape);
+cudaError_t launch_spmm_rowwalk(const SpmmLaunch& L, cudaStream_t st);  // row-walk tiles
+cudaError_t launch_spmm_rows(const SpmmLaunch& L, cudaStream_t st);     // any tiles, warp per row (general tiles, long rows)
+// out[i * ncols + k] = B[idx[i] - 1 + k * ldb]
+cudaError_t launch_pack_rows(int dtype, const void* B, i64 ldb, const i64* idx, i64 n, int ncols, void* out, cudaStream_t st);
+
 struct LongRowsLaunch {
     int dtype, itype;
     const void* rowptr;

@@ -143,6 +143,61 @@ extern "C" int hpcla_uniform_partition(int64_t n, int nranks, int64_t* out) {
     return HPCLA_OK;
 }
 
+// VectorRepartitionPlan(x, p) — src/vectors.jl:519-616.  Both partitions are known on every rank, so the plan is a pure
+// function (the reference's Alltoall of counts, :556-557, only tells a rank what it could compute itself).  Ranks
+// whose range in the other partition meets mine form one consecutive run: found by bisection, then walked.
+static int first_rank_reaching(const int64_t* part, int nranks, i64 g) {  // first rank r with part[r+1] > g
+    int lo = 0, hi = nranks;
+    while (lo < hi) {
+        const int mid = (lo + hi) / 2;
+        if (part[mid + 1] > g) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+extern "C" int hpcla_repartition_plan(int rank, int nranks, const int64_t* old_partition, const int64_t* new_partition, int64_t* n_send_out,
+                                      int64_t* send_rank_ids, int64_t* send_first, int64_t* send_count, int64_t* n_recv_out, int64_t* recv_rank_ids,
+                                      int64_t* recv_count, int64_t* recv_offset, int64_t* local_out /* [3]: src first, count, dst offset */,
+                                      int64_t* result_local_size_out) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || !old_partition || !new_partition || !n_send_out || !n_recv_out || !local_out || !result_local_size_out)
+        return fail(HPCLA_ERR_ARG, "hpcla_repartition_plan: bad arguments");
+    if (old_partition[0] != 1 || new_partition[0] != 1 || old_partition[nranks] != new_partition[nranks])
+        return fail(HPCLA_ERR_ARG, "hpcla_repartition_plan: partitions must start at 1 and cover the same %lld elements", (long long)(old_partition[nranks] - 1));
+    for (int r = 0; r < nranks; ++r)
+        if (old_partition[r + 1] < old_partition[r] || new_partition[r + 1] < new_partition[r]) return fail(HPCLA_ERR_ARG, "hpcla_repartition_plan: partitions must be non-decreasing");
+    const i64 src_b = old_partition[rank], src_e = old_partition[rank + 1];  // my elements today: [src_b, src_e)
+    const i64 dst_b = new_partition[rank], dst_e = new_partition[rank + 1];  // my elements afterwards
+    i64 ns = 0, nr = 0;
+    local_out[0] = 1, local_out[1] = 0, local_out[2] = 0;  // local_src_range = 1:0, local_dst_offset = 0 (:571-572)
+    if (src_e > src_b) {  // who receives my elements: ranks whose NEW range meets [src_b, src_e)
+        for (int r = first_rank_reaching(new_partition, nranks, src_b); r < nranks && new_partition[r] < src_e; ++r) {
+            const i64 b = std::max(src_b, new_partition[r]), e = std::min(src_e, new_partition[r + 1]);
+            if (e <= b) continue;
+            if (r == rank) {
+                local_out[0] = b - src_b + 1;
+                local_out[1] = e - b;
+                local_out[2] = b - dst_b + 1;
+            } else {
+                send_rank_ids[ns] = r, send_first[ns] = b - src_b + 1, send_count[ns] = e - b;
+                ++ns;
+            }
+        }
+    }
+    if (dst_e > dst_b) {  // who sends me elements: ranks whose OLD range meets [dst_b, dst_e)
+        for (int r = first_rank_reaching(old_partition, nranks, dst_b); r < nranks && old_partition[r] < dst_e; ++r) {
+            const i64 b = std::max(dst_b, old_partition[r]), e = std::min(dst_e, old_partition[r + 1]);
+            if (e <= b || r == rank) continue;
+            recv_rank_ids[nr] = r, recv_count[nr] = e - b, recv_offset[nr] = b - dst_b + 1;
+            ++nr;
+        }
+    }
+    *n_send_out = ns;
+    *n_recv_out = nr;
+    *result_local_size_out = dst_e - dst_b;
+    return HPCLA_OK;
+}
+
 // src/sparse.jl:501 (col_indices) and :137-144 (compress_AT)
 extern "C" int hpcla_compress_columns(int itype, int64_t nnz, const void* global_cols, int64_t ncols_global, void* colval_out,
                                       int64_t* col_indices_out, int64_t* ncc_out) {

@@ -142,11 +142,15 @@ class HPCSparseMatrix:
         return self.nzval if isinstance(self.nzval, np.ndarray) else self.nzval.detach().cpu().numpy()
 
     def __matmul__(self, x):
-        return matvec(self, x)
+        return self.__mul__(x)
 
     def __mul__(self, x):
         if isinstance(x, HPCVector):
             return matvec(self, x)
+        from .dense import HPCMatrix, spmm
+
+        if isinstance(x, HPCMatrix):  # Base.:*(A::HPCSparseMatrix, B::HPCMatrix) — src/sparse.jl:2391-2413
+            return spmm(self, x)
         return NotImplemented
 
     @property
@@ -306,12 +310,17 @@ def _comm_key(b: HPCBackend):
 
 def clear_plan_cache() -> None:
     """clear_plan_cache!() — src/HPCLinearAlgebra.jl:181-201."""
+    from . import vectors as _v
+
     _vector_plan_cache.clear()
+    _v._repartition_plan_cache.clear()
 
 
 def cache_sizes() -> Dict[str, int]:
     """cache_sizes() — src/HPCLinearAlgebra.jl:208-244 (only the cache this path owns)."""
-    return {"vector_plan": len(_vector_plan_cache)}
+    from . import vectors as _v
+
+    return {"vector_plan": len(_vector_plan_cache), "repartition_plan": len(_v._repartition_plan_cache)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -455,7 +464,11 @@ class Transpose:
     def __init__(self, parent: HPCSparseMatrix):
         self.parent = parent
 
-    def __matmul__(self, x: HPCVector) -> HPCVector:
+    def __matmul__(self, x):
+        from .dense import HPCMatrix, spmm
+
+        if isinstance(x, HPCMatrix):  # transpose(A) * B — src/sparse.jl:2420-2424: materialise A^T, then A^T * B
+            return spmm(materialize_transpose(self.parent), x)
         return transpose_matvec(self.parent, x)
 
     __mul__ = __matmul__

@@ -164,17 +164,104 @@ class HPCVector:
 # ---------------------------------------------------------------------------------------------------------------
 # reductions / updates on the device (src/vectors.jl:758-812, 1203-1221)
 # ---------------------------------------------------------------------------------------------------------------
-def _require_same_partition(x: HPCVector, y: HPCVector, what: str) -> None:
+# ---------------------------------------------------------------------------------------------------------------
+# repartition (src/vectors.jl:469-720): the step in front of the hot path whenever partitions differ
+# ---------------------------------------------------------------------------------------------------------------
+class VectorRepartitionPlan:
+    """VectorRepartitionPlan{T} (src/vectors.jl:491-506): the index fields (1-based, ranks ascending), computed by
+    hpcla_repartition_plan.  No buffers: the device exchange moves contiguous ranges in place."""
+
+    def __init__(self, rank: int, nranks: int, old_partition: np.ndarray, new_partition: np.ndarray):
+        op = np.ascontiguousarray(old_partition, dtype=np.int64)
+        npart = np.ascontiguousarray(new_partition, dtype=np.int64)
+        if len(npart) != nranks + 1 or len(op) != nranks + 1:
+            raise ValueError(f"repartition: a partition must have nranks+1 = {nranks + 1} entries")
+        a = [np.zeros(max(nranks, 1), dtype=np.int64) for _ in range(6)]
+        ns, nr, size = np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.int64)
+        self._local3 = np.zeros(3, dtype=np.int64)
+        _lib.check(_lib.lib().hpcla_repartition_plan(rank, nranks, _lib.ptr(op), _lib.ptr(npart), _lib.ptr(ns), _lib.ptr(a[0]), _lib.ptr(a[1]), _lib.ptr(a[2]),
+                                                     _lib.ptr(nr), _lib.ptr(a[3]), _lib.ptr(a[4]), _lib.ptr(a[5]), _lib.ptr(self._local3), _lib.ptr(size)))
+        ns, nr = int(ns[0]), int(nr[0])
+        self._send = [np.ascontiguousarray(v[:ns]) for v in a[:3]]
+        self._recv = [np.ascontiguousarray(v[:nr]) for v in a[3:]]
+        self.send_rank_ids = self._send[0].tolist()
+        self.send_ranges = [(int(f), int(f + c - 1)) for f, c in zip(self._send[1], self._send[2])]
+        self.recv_rank_ids = self._recv[0].tolist()
+        self.recv_counts = self._recv[1].tolist()
+        self.recv_offsets = self._recv[2].tolist()
+        f, c, o = (int(v) for v in self._local3)
+        self.local_src_range = (f, f + c - 1)
+        self.local_dst_offset = o
+        self.result_partition = npart.copy()
+        self.result_partition_hash = compute_partition_hash(npart)
+        self.result_local_size = int(size[0])
+
+
+_repartition_plan_cache = {}
+repartition_plan_build_count = 0
+
+
+def get_repartition_plan(x: HPCVector, p: np.ndarray) -> VectorRepartitionPlan:
+    """get_repartition_plan(x, p) — src/vectors.jl:684-693: memoised on (hash of x's partition, hash of p, T)."""
+    global repartition_plan_build_count
+    b = x.backend
+    key = (x.structural_hash, compute_partition_hash(p), np.dtype(b.T).str, comm_rank(b.comm), id(getattr(b.comm, "world", None)))
+    plan = _repartition_plan_cache.get(key)
+    if plan is None:
+        plan = _repartition_plan_cache[key] = VectorRepartitionPlan(comm_rank(b.comm), comm_size(b.comm), x.partition, p)
+        repartition_plan_build_count += 1
+    return plan
+
+
+def repartition(x: HPCVector, p) -> HPCVector:
+    """repartition(x, p) — src/vectors.jl:712-720.  Same partition: returns x itself (the reference's fast path)."""
+    p = np.ascontiguousarray(p, dtype=np.int64)
+    if x.partition is p or (len(x.partition) == len(p) and np.array_equal(x.partition, p)):
+        return x
+    if len(p) != comm_size(x.backend.comm) + 1 or p[0] != 1 or p[-1] != len(x) + 1:
+        raise ValueError(f"repartition: p must have nranks+1 entries, start at 1 and end at length(x)+1 = {len(x) + 1}")
+    b = x.backend
+    plan = get_repartition_plan(x, p)
+    if not b.is_cuda:
+        raise _lib.HPCLAError("repartition needs DeviceCUDA operands: this build moves data on the device only (no CPU fallback)")
+    import torch
+
+    out = torch.empty(plan.result_local_size, dtype=x.v.dtype, device=x.v.device)
+    ctx = b.ctx()
+    if ctx.world == "threads":
+        # single-process harness world: every rank publishes its slice, the receivers copy their ranges device to device
+        srcs = comm_allgather(b.comm, x.v)
+        f, l = plan.local_src_range
+        if l >= f:
+            out[plan.local_dst_offset - 1 : plan.local_dst_offset - 1 + (l - f + 1)].copy_(x.v[f - 1 : l])
+        me = comm_rank(b.comm)
+        for r, cnt, off in zip(plan.recv_rank_ids, plan.recv_counts, plan.recv_offsets):
+            peer = VectorRepartitionPlan(r, comm_size(b.comm), x.partition, p)  # where my range starts in r's slice
+            pf = peer.send_ranges[peer.send_rank_ids.index(me)][0]
+            out[off - 1 : off - 1 + cnt].copy_(srcs[r][pf - 1 : pf - 1 + cnt])
+        torch.cuda.synchronize(x.v.device)
+        comm_allgather(b.comm, 0)  # nobody drops its slice before every reader is done
+    else:
+        s, r = plan._send, plan._recv
+        _lib.check(_lib.lib().hpcla_repartition_run(ctx.handle, _lib.dtype_code(b.T), len(plan.send_rank_ids), _lib.ptr(s[0]), _lib.ptr(s[1]), _lib.ptr(s[2]),
+                                                    len(plan.recv_rank_ids), _lib.ptr(r[0]), _lib.ptr(r[1]), _lib.ptr(r[2]), _lib.ptr(plan._local3),
+                                                    _lib.ptr(x.v), _lib.ptr(out), _current_stream(b)))
+    return HPCVector(plan.result_partition_hash, plan.result_partition, out, b)
+
+
+def _aligned(x: HPCVector, y: HPCVector) -> HPCVector:
+    """y on x's partition — what the reference does in front of dot and the vector updates when partitions differ
+    (src/vectors.jl:806-811, 873-876)."""
     assert_backends_compatible(x.backend, y.backend)
-    if x.structural_hash != y.structural_hash:
-        # the reference falls back to repartition(y, x.partition) (src/vectors.jl:806-811); that path is a
-        # "next" row, not part of this build
-        raise NotImplementedError(f"{what}: operands have different partitions; repartition is outside the SpMV hot path")
+    if len(x) != len(y):
+        raise ValueError(f"DimensionMismatch: lengths {len(x)} and {len(y)}")
+    return y if x.structural_hash == y.structural_hash else repartition(y, x.partition)
 
 
 def dot(x: HPCVector, y: HPCVector):
-    """LinearAlgebra.dot(x, y) — src/vectors.jl:798-812: local dot (conjugating x) + Allreduce(+)."""
-    _require_same_partition(x, y, "dot")
+    """LinearAlgebra.dot(x, y) — src/vectors.jl:798-812: local dot (conjugating x) + Allreduce(+); y is repartitioned
+    to x's partition first when they differ (:806-811)."""
+    y = _aligned(x, y)
     b = x.backend
     ctx = b.ctx()
     code = _lib.dtype_code(b.T)
@@ -203,8 +290,9 @@ def norm(x: HPCVector, p=2):
 
 
 def axpby(alpha, x: HPCVector, beta, y: HPCVector) -> HPCVector:
-    """y .= alpha .* x .+ beta .* y (the fused broadcast of src/vectors.jl:1203-1221), in place on y."""
-    _require_same_partition(x, y, "axpby")
+    """y .= alpha .* x .+ beta .* y (the fused broadcast of src/vectors.jl:1203-1221), in place on y; x is
+    repartitioned to y's partition first when they differ."""
+    x = _aligned(y, x)
     b = x.backend
     a = np.array([alpha], dtype=b.T)
     c = np.array([beta], dtype=b.T)

@@ -289,6 +289,76 @@ def matvec(locals_: Sequence[LocalMatrix], x_global: np.ndarray, x_partition=Non
     return np.concatenate([spmv_local(locals_[r], gs[r]) for r in range(P)])
 
 
+def repartition_plan(rank: int, old_partition, new_partition) -> dict:
+    """VectorRepartitionPlan(x, p) — src/vectors.jl:519-616, restated loop for loop (1-based values)."""
+    xp = np.asarray(old_partition, dtype=np.int64)
+    p = np.asarray(new_partition, dtype=np.int64)
+    nranks = len(p) - 1
+    src_start, src_end = int(xp[rank]), int(xp[rank + 1]) - 1
+    dst_start, dst_end = int(p[rank]), int(p[rank + 1]) - 1
+    send_ranges_map = {}
+    for r in range(nranks):  # :536-552
+        r_start, r_end = int(p[r]), int(p[r + 1]) - 1
+        if r_end < r_start:
+            continue
+        o_start, o_end = max(src_start, r_start), min(src_end, r_end)
+        if o_start <= o_end:
+            send_ranges_map[r] = (o_start - src_start + 1, o_end - src_start + 1)
+    # :555-557 — the Alltoall of counts: rank r's count for me is the overlap of ITS source range with MY target range
+    recv_counts_raw = []
+    for r in range(nranks):
+        s_start, s_end = int(xp[r]), int(xp[r + 1]) - 1
+        if dst_end < dst_start:
+            recv_counts_raw.append(0)
+            continue
+        o_start, o_end = max(s_start, dst_start), min(s_end, dst_end)
+        recv_counts_raw.append(max(0, o_end - o_start + 1))
+    local_src, local_dst_offset = (1, 0), 0  # 1:0
+    if rank in send_ranges_map:  # :575-582
+        local_src = send_ranges_map[rank]
+        local_dst_offset = (src_start + local_src[0] - 1) - dst_start + 1
+    send_rank_ids = [r for r in range(nranks) if r in send_ranges_map and r != rank]
+    send_ranges = [send_ranges_map[r] for r in send_rank_ids]
+    recv_rank_ids, recv_counts, recv_offsets = [], [], []
+    for r in range(nranks):  # :594-608
+        if recv_counts_raw[r] > 0 and r != rank:
+            recv_rank_ids.append(r)
+            recv_counts.append(recv_counts_raw[r])
+            recv_offsets.append(max(int(xp[r]), dst_start) - dst_start + 1)
+    return dict(send_rank_ids=send_rank_ids, send_ranges=send_ranges, recv_rank_ids=recv_rank_ids, recv_counts=recv_counts,
+                recv_offsets=recv_offsets, local_src_range=local_src, local_dst_offset=local_dst_offset,
+                result_local_size=max(0, dst_end - dst_start + 1))
+
+
+def repartition(xs: Sequence[np.ndarray], old_partition, new_partition) -> List[np.ndarray]:
+    """execute_plan!(plan::VectorRepartitionPlan, x) on all ranks — src/vectors.jl:624-676 (messages = array moves)."""
+    P = len(xs)
+    plans = [repartition_plan(r, old_partition, new_partition) for r in range(P)]
+    out = [np.empty(pl["result_local_size"], dtype=xs[0].dtype) for pl in plans]
+    mail = {}
+    for r, pl in enumerate(plans):
+        a, b = pl["local_src_range"]
+        if b >= a:
+            out[r][pl["local_dst_offset"] - 1 : pl["local_dst_offset"] - 1 + (b - a + 1)] = xs[r][a - 1 : b]
+        for dest, (a, b) in zip(pl["send_rank_ids"], pl["send_ranges"]):
+            mail[(r, dest)] = xs[r][a - 1 : b].copy()
+    for r, pl in enumerate(plans):
+        for src, cnt, off in zip(pl["recv_rank_ids"], pl["recv_counts"], pl["recv_offsets"]):
+            buf = mail[(src, r)]
+            assert len(buf) == cnt
+            out[r][off - 1 : off - 1 + cnt] = buf
+    return out
+
+
+def matmat(locals_: Sequence[LocalMatrix], B_global: np.ndarray, b_row_partition=None) -> np.ndarray:
+    """A * B for a dense B, the reference's way (src/sparse.jl:2391-2413): for every column k, `A * B[:, k]` with the
+    column's partition = B's row partition (src/indexing.jl:385-393), results concatenated column by column."""
+    B_global = np.asarray(B_global)
+    cols = [matvec(locals_, B_global[:, k], b_row_partition) for k in range(B_global.shape[1])]
+    nrows = int(locals_[0].row_partition[-1]) - 1
+    return np.stack(cols, axis=1) if cols else np.zeros((nrows, 0), dtype=locals_[0].nzval.dtype)
+
+
 def transpose(locals_: Sequence[LocalMatrix]) -> List[LocalMatrix]:
     """HPCSparseMatrix(transpose(A)): TransposePlan + execute_plan! on all ranks (src/sparse.jl:1551-1829)."""
     L = lib()

@@ -56,6 +56,12 @@ def main():
         assert relerr(y.to_global(), ref) <= TOL[np.dtype(T)], ("A*x", kind, relerr(y.to_global(), ref))
         assert relerr(y2.to_global(), ref) <= TOL[np.dtype(T)]
         assert relerr(yT.to_global(), refT) <= TOL[np.dtype(T)]
+        # sparse x dense: one exchange for all columns (row-major ghost rows straight from NCCL), 4 columns per pass
+        Bg = np.stack([S.vector_local(T, S.X_SEED + j, 0, n) for j in range(6)], axis=1)
+        C = A * la.HPCMatrix.from_global(Bg, b)
+        Cg = C.to_global()
+        assert relerr(Cg, orc.matmat(olocs, Bg)) <= TOL[np.dtype(T)], ("A*B", kind)
+        assert np.array_equal(Cg[:, 0], y.to_global()), ("A*B column 0 vs A*x", kind)
         W = orc.PlanWorld(olocs, orc.uniform_partition(n, P))
         assert np.array_equal(g.cpu().numpy(), W.execute(orc.split_vector(xh, orc.uniform_partition(n, P)))[rank])
         W.close()
@@ -80,6 +86,19 @@ def main():
         olocs = orc.distribute(R, P, itype="i32" if Ti == np.int32 else "i64")
         assert relerr(y.to_global(), orc.matvec(olocs, xh, xp)) <= TOL[np.dtype(T)]
         assert la.spmv_info(A, x)["sends_contiguous"] == 0
+    # 2b. repartition over NCCL: contiguous ranges straight between device buffers
+    for T in (np.float64, np.complex128):
+        b = la.backend_cuda_mpi(T, np.int64, comm=comm, device=local_rank)
+        n = 5000
+        vh = np.random.default_rng(9).uniform(-1, 1, n).astype(T)
+        old = np.concatenate([[1], np.sort(np.random.default_rng(10).integers(1, n + 2, size=P - 1)), [n + 1]]).astype(np.int64)
+        new = np.concatenate([[1], np.sort(np.random.default_rng(11).integers(1, n + 2, size=P - 1)), [n + 1]]).astype(np.int64)
+        xv = la.HPCVector.from_global(vh, b, partition=old)
+        yv = la.repartition(xv, new)
+        assert yv.partition.tolist() == new.tolist() and np.array_equal(yv.to_global(), vh)
+        assert np.array_equal(yv.local_values(), orc.repartition(orc.split_vector(vh, old), old, new)[rank])
+        zv = la.HPCVector.from_global(vh, b, partition=new)
+        assert abs(la.dot(xv, zv) - np.vdot(vh, vh)) <= 1e-9 * n
     # 3. reductions + CG over NCCL
     b = la.backend_cuda_mpi(np.float64, np.int32, comm=comm, device=local_rank)
     N = 20

@@ -368,3 +368,105 @@ def test_staged_multiply_matches_device_multiply(case, monkeypatch):
         torch.cuda.synchronize()
         assert np.array_equal(yh.numpy(), y_ref)
         assert np.array_equal(y2.local_values(), y_ref) and torch.equal(x2.v.cpu(), xh)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sparse x dense: A * B::HPCMatrix in one library call vs the reference's column-by-column loop
+# ---------------------------------------------------------------------------------------------------------------
+def _spmm_body(rank, bs, A_global, B_global, row_partition, b_row_partition):
+    b = bs[rank]
+    torch.cuda.set_device(b.torch_device())
+    A = la.HPCSparseMatrix.from_global(A_global, b, row_partition=row_partition)
+    B = la.HPCMatrix.from_global(B_global, b, row_partition=b_row_partition)
+    C = A * B
+    assert isinstance(C, la.HPCMatrix) and C.row_partition.tolist() == A.row_partition.tolist()
+    assert C.col_partition.tolist() == la.uniform_partition(B_global.shape[1], len(bs)).tolist()
+    assert C.A.shape == (A.nrows_local, B_global.shape[1]) and (C.A.shape[0] <= 1 or C.A.stride(0) == 1)
+    cols = [(A * B.column(k)).to_global() for k in range(B_global.shape[1])]  # the reference's loop, on the device
+    CT = la.transpose(A) * la.HPCMatrix.from_global(np.resize(B_global, (A_global.shape[0], B_global.shape[1])), b, row_partition=A.row_partition)
+    return C.to_global(), np.stack(cols, axis=1), CT.to_global(), la.spmv_info(A, B.column(0))
+
+
+@pytest.mark.parametrize("case", ["poisson", "stencil27c", "ragged", "powerlaw", "laplace2d_f32"])
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_sparse_times_dense(case, P):
+    rng = np.random.default_rng(100 + P)
+    S = la.synth
+    rowp = bpart = None
+    if case == "poisson":
+        T, Ti, ncols = np.float64, np.int32, 6
+        rp, c, v = S.stencil_local(1, 24, 0, 24**3, T, Ti)
+        A = sp.csr_matrix((v, c - 1, rp - 1), shape=(24**3, 24**3))
+    elif case == "stencil27c":
+        T, Ti, ncols = np.complex128, np.int64, 5
+        rp, c, v = S.stencil_local(2, 14, 0, 14**3, T, Ti)
+        A = sp.csr_matrix((v, c - 1, rp - 1), shape=(14**3, 14**3))
+    elif case == "laplace2d_f32":
+        T, Ti, ncols = np.float32, np.int32, 9
+        rp, c, v = S.stencil_local(0, (90, 70), 0, 6300, T, Ti)
+        A = sp.csr_matrix((v, c - 1, rp - 1), shape=(6300, 6300))
+    elif case == "ragged":
+        T, Ti, ncols = np.float64, np.int32, 7
+        A = _ragged(rng, 3000, 2500, 0.004, T, long_rows=((5, 1700),))
+        cuts = np.sort(rng.integers(1, 2501, size=P - 1))
+        bpart = np.concatenate([[1], cuts, [2501]]).astype(np.int64)  # B's rows partitioned unlike A's columns
+    else:
+        T, Ti, ncols = np.float32, np.int32, 4
+        n = 40000
+        rp, c, v = S.powerlaw_local(n, 0xC4, 30000, 0, n, T, Ti)
+        A = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    A = sp.csr_matrix(A).astype(T)
+    Bg = rng.uniform(-1, 1, (A.shape[1], ncols)).astype(T)
+    if np.dtype(T) == np.complex128:
+        Bg = Bg + 1j * rng.uniform(-1, 1, Bg.shape)
+    la.clear_plan_cache()
+    res = spmd(backends(P, T, Ti), _spmm_body, A, Bg, rowp, bpart)
+    itype = "i32" if Ti == np.int32 else "i64"
+    olocs = orc.distribute(A, P, itype=itype)
+    C_ref = orc.matmat(olocs, Bg, bpart)
+    BT = np.resize(Bg, (A.shape[0], ncols))
+    CT_ref = orc.matmat(orc.transpose(olocs), BT)
+    for C, cols, CT, info in res:
+        assert relerr(C, C_ref) <= TOL[np.dtype(T)] and relerr(CT, CT_ref) <= TOL[np.dtype(T)]
+        assert relerr(C, cols) <= TOL[np.dtype(T)]
+        if case in ("poisson", "laplace2d_f32"):
+            assert info["lanes_per_row"] == 1 and np.array_equal(C, C_ref), "one lane per row: the reference's summation order, every column"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# repartition on the device and the partition-mismatch fallbacks of dot / axpby
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", [np.float64, np.complex128, np.float32])
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_repartition_and_mismatched_partitions(T, P):
+    rng = np.random.default_rng(7 + P)
+    n = 1000
+    v = rng.uniform(-1, 1, n).astype(T)
+    w = rng.uniform(-1, 1, n).astype(T)
+    if np.dtype(T).kind == "c":
+        v = v + 1j * rng.uniform(-1, 1, n)
+    old = np.concatenate([[1], np.sort(rng.integers(1, n + 2, size=P - 1)), [n + 1]]).astype(np.int64)
+    new = np.concatenate([[1], np.sort(rng.integers(1, n + 2, size=P - 1)), [n + 1]]).astype(np.int64)
+    if P > 1:
+        new[1] = new[0]  # an empty rank in the target partition
+
+    def body(rank, bs):
+        b = bs[rank]
+        torch.cuda.set_device(b.torch_device())
+        x = la.HPCVector.from_global(v, b, partition=old)
+        y = la.repartition(x, new)
+        assert y.partition.tolist() == new.tolist() and y.v.is_cuda and y.local_size == int(new[rank + 1] - new[rank])
+        assert la.repartition(x, old) is x  # the reference's fast path (test/test_repartition.jl:67-69)
+        n0 = la.vectors.repartition_plan_build_count
+        y2 = la.repartition(x, new)
+        assert la.vectors.repartition_plan_build_count == n0 and y2.structural_hash == y.structural_hash
+        z = la.HPCVector.from_global(w, b, partition=new)
+        d = la.dot(x, z)  # z is repartitioned to x's partition (src/vectors.jl:806-811)
+        la.axpby(2.0, x, 1.0, z)  # x is repartitioned to z's
+        return y.to_global(), d, z.to_global()
+
+    la.clear_plan_cache()
+    for yg, d, zg in spmd(backends(P, T, np.int64), body):
+        assert np.array_equal(yg, v)
+        assert abs(d - np.vdot(v, w)) <= (1e-3 if T == np.float32 else 1e-10) * n
+        assert relerr(zg, 2 * v + w) <= TOL[np.dtype(T)]

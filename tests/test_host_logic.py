@@ -298,3 +298,80 @@ def test_gloo_world_size_2():
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("DIST_OK") == 2
+
+
+def test_hpcmatrix_structure_and_no_cpu_product():
+    """HPCMatrix constructors (src/dense.jl:125-202) on a structure-only backend; A*B refuses to compute on the CPU."""
+    P = 3
+    bs = la.backends_threads(P, np.float64, np.int64, cuda=False)
+    M = np.arange(7 * 4, dtype=np.float64).reshape(7, 4)
+    R = sp.random(5, 7, density=0.5, random_state=np.random.default_rng(3), format="csr")
+
+    def body(rank, bs):
+        b = bs[rank]
+        B = la.HPCMatrix.from_global(M, b)
+        assert B.row_partition.tolist() == orc.uniform_partition(7, P).tolist() and B.col_partition.tolist() == orc.uniform_partition(4, P).tolist()
+        lo, hi = int(B.row_partition[rank]) - 1, int(B.row_partition[rank + 1]) - 1
+        assert np.array_equal(B.local_values(), M[lo:hi]) and B.shape == (7, 4)
+        col = B.column(2)
+        assert col.partition.tolist() == B.row_partition.tolist() and np.array_equal(col.local_values(), M[lo:hi, 2])
+        B2 = la.HPCMatrix_local(M[lo:hi], b)
+        assert B2.row_partition.tolist() == B.row_partition.tolist() and np.array_equal(B2.to_global(), M)
+        with pytest.raises(IndexError):
+            B.column(4)
+        A = la.HPCSparseMatrix.from_global(R, b)
+        with pytest.raises(la.HPCLAError):
+            A * B
+        return True
+
+    assert all(bs[0].comm.world.run(body, bs))
+
+
+def test_oracle_matmat_is_the_column_loop():
+    rng = np.random.default_rng(11)
+    R = sp.random(40, 30, density=0.2, random_state=rng, format="csr")
+    Bg = rng.uniform(-1, 1, (30, 5))
+    for P in (1, 3):
+        C = orc.matmat(orc.distribute(R, P), Bg)
+        assert np.linalg.norm(C - R @ Bg) <= 1e-13 * np.linalg.norm(R @ Bg)
+
+
+def _reference_test_partition(n, nranks):
+    """The non-uniform target partition test/test_repartition.jl:44-57 builds (1-based starts)."""
+    if nranks < 2:
+        return orc.uniform_partition(n, nranks)
+    p, total = [1], 0
+    for r in range(nranks):
+        count = n // nranks - 1 + (1 if r < n % nranks else 0) if r < nranks - 1 else n - total
+        total += count
+        p.append(total + 1)
+    return np.asarray(p, dtype=np.int64)
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 7])
+def test_repartition_plan_matches_the_restatement(P):
+    """hpcla_repartition_plan (bisection over the partitions) == the loop-for-loop restatement of
+    VectorRepartitionPlan (src/vectors.jl:519-616), every field, including empty ranks; and the restated execute
+    moves the data where the reference's own test expects it (test/test_repartition.jl:38-62)."""
+    rng = np.random.default_rng(50 + P)
+    cases = [(12, orc.uniform_partition(12, P), _reference_test_partition(12, P))]
+    for _ in range(30):
+        n = int(rng.integers(0, 40))
+        old = np.concatenate([[1], np.sort(rng.integers(1, n + 2, size=P - 1)), [n + 1]]).astype(np.int64)
+        new = np.concatenate([[1], np.sort(rng.integers(1, n + 2, size=P - 1)), [n + 1]]).astype(np.int64)
+        cases.append((n, old, new))
+    for n, old, new in cases:
+        for r in range(P):
+            got = la.VectorRepartitionPlan(r, P, old, new)
+            ref = orc.repartition_plan(r, old, new)
+            assert got.send_rank_ids == ref["send_rank_ids"] and got.send_ranges == ref["send_ranges"]
+            assert got.recv_rank_ids == ref["recv_rank_ids"] and got.recv_counts == ref["recv_counts"] and got.recv_offsets == ref["recv_offsets"]
+            assert got.result_local_size == ref["result_local_size"] and got.local_dst_offset == ref["local_dst_offset"]
+            a, b = ref["local_src_range"]
+            assert got.local_src_range == ((a, b) if b >= a else (1, 0))
+        v = np.arange(1.0, n + 1)
+        out = orc.repartition(orc.split_vector(v, old), old, new)
+        assert np.array_equal(np.concatenate(out) if out else v, v)
+        assert [len(o) for o in out] == np.diff(new).tolist()
+    with pytest.raises(la.HPCLAError):
+        la.VectorRepartitionPlan(0, P, orc.uniform_partition(5, P), orc.uniform_partition(6, P))
