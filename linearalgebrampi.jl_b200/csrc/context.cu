@@ -110,6 +110,7 @@ struct hpcla_csr {
     i64 ntiles = 0;
     std::vector<unsigned char> tile_class;  // per tile: 0 no rows, 1 row-walk kernel, 2 general kernel
     std::vector<TileDesc> h_tiles;          // host copy of the tile table [ntiles+1]
+    unsigned char* d_hdrs = nullptr;        // tile headers of the direct row walk (ntiles * shape.hdr_bytes), or null
     i64 n_class[3] = {0, 0, 0};
     i64 long_threshold = 0, chunk_nnz = 0;
     i64 nlong = 0, nchunks = 0;
@@ -372,6 +373,25 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         for (unsigned char c : A->tile_class) A->n_class[c] += 1;
         if (irregular || kind == 1 || A->n_class[1] >= A->n_class[2]) break;
     }
+    // Tile headers of the direct row walk.  Measured (profiles/r1h_tune_direct_walk.txt): it wins where its 16-bit row
+    // offsets replace 8-byte row pointers (Int64 indices: 338 -> 327 us on Poisson 256^3) and for real-valued multi-lane
+    // walks (27-point Float64: 405 -> 371 us); it loses where registers are the scarce resource (one lane per row at 8
+    // CTAs per SM: 264 -> 267..282 us; ComplexF64: 640 -> 662 us).  HPCLA_DIRECT=0|1 overrides.
+    {
+        const char* e = getenv("HPCLA_DIRECT");
+        bool direct = itype == HPCLA_I64 || (dtype != HPCLA_C128 && A->shape.lanes >= 2);
+        if (e) direct = e[0] != '0';
+        if (direct && A->shape.hdr_rows > 0 && A->n_class[1] > 0) {
+            unsigned char* d_cls = nullptr;
+            CU_TRY(cudaMalloc(&d_cls, (size_t)A->ntiles));
+            CU_TRY(cudaMemcpyAsync(d_cls, A->tile_class.data(), (size_t)A->ntiles, cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMalloc(&A->d_hdrs, (size_t)A->ntiles * (size_t)A->shape.hdr_bytes));
+            CU_TRY(cudaMemsetAsync(A->d_hdrs, 0, (size_t)A->ntiles * (size_t)A->shape.hdr_bytes, st));
+            CU_TRY(launch_build_tile_headers(itype, d_rowptr, A->d_tiles, d_cls, A->ntiles, A->shape.window, A->shape.hdr_bytes, A->d_hdrs, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(d_cls);
+        }
+    }
     // rows longer than the split threshold (rare: power-law tails)
     const i64 cap = nnz / A->long_threshold + 1;
     unsigned long long* d_count = nullptr;
@@ -432,6 +452,7 @@ extern "C" void hpcla_csr_destroy(hpcla_csr* A) {
     if (!A) return;
     cudaSetDevice(A->ctx->device);
     cudaFree(A->d_tiles);
+    cudaFree(A->d_hdrs);
     cudaFree(A->d_long_rows);
     cudaFree(A->d_chunk_ptr);
     cudaFree(A->d_partials);
@@ -706,6 +727,26 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
     L.has_ghost = op->has_ghost;
     L.y = d_y;
     L.long_threshold = A->long_threshold;
+    L.hdrs = A->d_hdrs;
+}
+
+// Positions [lo, hi) of an ascending tile list as at most 8 runs of consecutive tiles (the direct row walk's launch
+// description).  False when the slice is more fragmented than that.
+static bool direct_runs(const std::vector<int>& list, int lo, int hi, SpmvLaunch& L) {
+    int n = 0;
+    for (int q = lo; q < hi;) {
+        if (n == 8) return false;
+        int q1 = q + 1;
+        while (q1 < hi && list[(size_t)q1] == list[(size_t)q1 - 1] + 1) ++q1;
+        L.run_cta0[n] = q - lo;
+        L.run_tile0[n] = list[(size_t)q];
+        ++n;
+        q = q1;
+    }
+    for (int j = n; j <= 8; ++j) L.run_cta0[j] = hi - lo;
+    for (int j = n; j < 8; ++j) L.run_tile0[j] = 0;
+    L.n_runs = n;
+    return n > 0;
 }
 
 // both kernel classes over the interior (which = 0) or boundary (which = 1) tiles
@@ -717,7 +758,8 @@ static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t s
         L.tile0 = op->list_tile0[c][which] >= 0 ? op->list_tile0[c][which] + lo : -1;
         L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
-        if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
+        if (c == 0 && !L.has_ghost && op->csr->d_hdrs && direct_runs(op->h_list[0][which], lo, hi, L)) CU_TRY(launch_spmv_direct(L, stream));
+        else if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
         else CU_TRY(launch_spmv_general(L, stream));
         op->launches += 1;
     }

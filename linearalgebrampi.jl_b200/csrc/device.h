@@ -26,10 +26,14 @@ struct TileShape {
     int cap;            // row walk: staged nonzeros per tile (window + slack, multiple of 4)
     int rp_cap;         // row walk: staged row pointers per tile (multiple of 4)
     int general_elems;  // general kernel: products staged per tile
+    int ovf;            // direct row walk: entries past the window fetched unconditionally
+    int hdr_rows;       // direct row walk: rows a tile header can describe (0: no direct walk for this shape)
+    int hdr_bytes;      // direct row walk: bytes per tile header (multiple of 16)
 };
 // avg_row: typical stored entries per row (the most common row length, else the mean); irregular: general kernel only; overrides: 0 = none (tuning hooks)
 TileShape tile_shape(int dtype, int itype, double avg_row, bool irregular, int lanes_override, int window_override);
 size_t rowwalk_smem_bytes(int dtype, int itype, const TileShape& shape);
+size_t direct_smem_bytes(int dtype, int itype, const TileShape& shape);
 
 struct SpmvLaunch {
     int dtype, itype;
@@ -40,6 +44,11 @@ struct SpmvLaunch {
     TileShape shape;        // as fixed when the tile table was built
     const TileRec* recs;    // [n_launch] the tiles of this launch, one CTA each
     i64 tile0 = -1;         // >= 0: recs are the consecutive tiles tile0, tile0 + 1, ...
+    // direct row walk: the launch as <= 8 runs of consecutive tiles (run j = CTAs run_cta0[j] .. run_cta0[j+1]-1)
+    const unsigned char* hdrs = nullptr;
+    int n_runs = 0;
+    int run_cta0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int run_tile0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int n_launch;
     // x addressing for a 1-based compressed column c:
     //   own  <=> own_lo <= c < own_lo + own_n           -> x_own[c - own_lo]   (x_own already offset to the first own source)
@@ -69,6 +78,9 @@ cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc*
 cudaError_t launch_tile_maxcol(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n, i64* out, cudaStream_t st);
 cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 1
 cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 2
+cudaError_t launch_spmv_direct(const SpmvLaunch& L, cudaStream_t st);   // tiles of class 1, ghost-free, as runs of consecutive tiles
+cudaError_t launch_build_tile_headers(int itype, const void* rowptr, const TileDesc* tiles, const unsigned char* cls, i64 ntiles, int window, int hdr_bytes,
+                                      unsigned char* hdrs, cudaStream_t st);
 
 // Sparse x dense: kn (1 or 4) columns k0 .. k0+kn of C = A * B over the tiles of `recs`.
 struct SpmmLaunch {

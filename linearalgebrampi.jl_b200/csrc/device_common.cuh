@@ -58,6 +58,23 @@ __device__ __forceinline__ cplx ld_x(const cplx* p) {
     double2 t = __ldg(reinterpret_cast<const double2*>(p));
     return cplx{t.x, t.y};
 }
+// the same loads as volatile asm: the compiler may not sink them below a later barrier wait (plain ld.global.nc loads
+// are "invariant" and do get moved across asm memory clobbers)
+__device__ __forceinline__ float ld_x_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_x_pinned(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ cplx ld_x_pinned(const cplx* p) {
+    cplx v;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "l"(p));
+    return v;
+}
 // streaming (evict-first) scalar loads of the matrix, for the unaligned / tail cases
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }

@@ -131,6 +131,162 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - (GHOST ? 1 : 0)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Row walk, direct form: NO dependent load in front of any copy.  A launch is a handful of runs of consecutive tiles
+// (TileRuns, by value), so the CTA's tile — hence its window of the nonzero stream — is arithmetic; the per-tile
+// HEADER (first row, row count, staged length and the row offsets as 16-bit values relative to the window: a
+// library-owned, re-blocked copy of the row-pointer slice at a fixed stride) is arithmetic too.  Thread 0 issues
+// everything at once on two mbarriers: A = column indices + header, B = values.  When A lands the lanes issue their x
+// gathers; those fly while the values are still landing; when B lands only shared-memory reads and the arithmetic are
+// left.  The (rare) rows that overrun the unconditional over-fetch get a second, conditional copy.
+// ------------------------------------------------------------------------------------------------------------------
+struct TileRuns {
+    int n;         // runs in use (<= 8)
+    int cta0[9];   // run j covers CTAs cta0[j] .. cta0[j+1]-1
+    int tile0[8];  // first tile of run j
+};
+
+template <class T, class Ti>
+struct DirectArgs {
+    const Ti* colval;
+    const T* nzval;
+    const unsigned char* hdrs;  // per tile, hdr_bytes apart: {i64 r0; i32 nrows; i32 n_st; u16 off[nrows+1]}
+    XView<T> xv;
+    T* y;
+    i64 nnz_total;
+    TileRuns runs;
+    int window, ovf, hdr_bytes;
+};
+
+#ifndef HPCLA_DIRECT_CTAS_DROP
+#define HPCLA_DIRECT_CTAS_DROP 0  // A/B knob: allocate registers for this many fewer resident CTAs
+#endif
+#ifndef HPCLA_DIRECT_ONE_BARRIER
+#define HPCLA_DIRECT_ONE_BARRIER 0  // A/B knob: values on the same barrier as the column indices (no early gathers)
+#endif
+template <class T, class Ti, int G>
+__global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - HPCLA_DIRECT_CTAS_DROP) spmv_rowwalk_direct_kernel(const DirectArgs<T, Ti> a, int cap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* barA = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* barB = barA + 1;
+    const unsigned char* shdr = smem_raw + 16;
+    Ti* scol = reinterpret_cast<Ti*>(smem_raw + 16 + a.hdr_bytes);
+    T* sval = reinterpret_cast<T*>(scol + cap);
+    const int tid = threadIdx.x;
+    // my tile: a short compare chain over kernel parameters
+    int run = 0;
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+        if (j < a.runs.n && (int)blockIdx.x >= a.runs.cta0[j]) run = j;
+    const i64 tile = (i64)a.runs.tile0[run] + ((int)blockIdx.x - a.runs.cta0[run]);
+    const i64 w0 = tile * (i64)a.window;
+    const i64 left = (a.nnz_total - w0) & ~(i64)3;
+    const int want = a.window + a.ovf;
+    const int n_fetch = (int)(left < (i64)want ? (left > 0 ? left : 0) : (i64)want);  // multiple of 4
+    uint64_t pol = 0;
+    if (tid == 0) {
+        mbar_init(barA, 1);
+        mbar_init(barB, 1);
+        mbar_fence_init();
+        pol = l2_evict_first_policy();
+        mbar_expect_tx(barA, (uint32_t)n_fetch * (uint32_t)sizeof(Ti) + (uint32_t)a.hdr_bytes);
+        bulk_g2s(const_cast<unsigned char*>(shdr), a.hdrs + tile * (i64)a.hdr_bytes, (uint32_t)a.hdr_bytes, barA, pol);
+        if (n_fetch > 0) bulk_g2s(scol, a.colval + w0, (uint32_t)n_fetch * (uint32_t)sizeof(Ti), barA, pol);
+        mbar_expect_tx(barB, (uint32_t)n_fetch * (uint32_t)sizeof(T));
+        if (n_fetch > 0) bulk_g2s(sval, a.nzval + w0, (uint32_t)n_fetch * (uint32_t)sizeof(T), barB, pol);
+    }
+    __syncthreads();  // barriers initialised before anyone waits
+#if HPCLA_DIRECT_ONE_BARRIER
+    mbar_wait(barB, 0);
+#endif
+    mbar_wait(barA, 0);
+    const i64 r0 = *reinterpret_cast<const i64*>(shdr);
+    const int nrows = *reinterpret_cast<const int*>(shdr + 8);
+    const int n_st = *reinterpret_cast<const int*>(shdr + 12);
+    const unsigned short* off = reinterpret_cast<const unsigned short*>(shdr + 16);
+    if (n_st > n_fetch) {  // uniform, rare: a last row that overruns the over-fetch, or the unaligned tail of the arrays
+        const i64 avail = (a.nnz_total - w0 - n_fetch) & ~(i64)3;
+        i64 more = ((i64)(n_st - n_fetch) + 3) & ~(i64)3;
+        if (more > avail) more = avail;
+        __syncthreads();  // everybody has passed the phase-0 wait of barA before it is re-armed
+        if (tid == 0) {
+            mbar_expect_tx(barA, (uint32_t)more * (uint32_t)(sizeof(Ti) + sizeof(T)));
+            if (more > 0) {
+                bulk_g2s(scol + n_fetch, a.colval + w0 + n_fetch, (uint32_t)more * (uint32_t)sizeof(Ti), barA, pol);
+                bulk_g2s(sval + n_fetch, a.nzval + w0 + n_fetch, (uint32_t)more * (uint32_t)sizeof(T), barA, pol);
+            }
+        }
+        for (int k = n_fetch + (int)more + tid; k < n_st; k += ROW_THREADS) {
+            scol[k] = a.colval[w0 + k];
+            sval[k] = a.nzval[w0 + k];
+        }
+        __syncthreads();
+        mbar_wait(barA, 1);
+    }
+    constexpr int RPP = ROW_THREADS / G;
+    constexpr int B = HPCLA_WALK_BATCH;
+    const int lane = tid % G;
+    bool values_in = false;
+    for (int base = 0; base < nrows; base += RPP) {
+        const int i = base + tid / G;
+        const bool valid = i < nrows;
+        const int b = valid ? (int)off[i] : 0;
+        const int e = valid ? (int)off[i + 1] : 0;
+        int k = b + lane;
+        T xg[B];  // the gathers go out as soon as the columns are in ...
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int kk = k + u * G;
+            xg[u] = el_zero(T());
+            if (kk < e) xg[u] = ld_x_pinned(a.xv.own + (i64)scol[kk]);
+        }
+        if (!values_in) {  // ... and fly while the values are still landing
+            mbar_wait(barB, 0);
+            values_in = true;
+        }
+        T acc = el_zero(T());
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+            if (k + u * G < e) acc = el_add(acc, el_mul(sval[k + u * G], xg[u]));
+        for (k += B * G; k < e; k += B * G) {  // rows longer than B * G entries
+            T p[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int kk = k + u * G;
+                p[u] = (kk < e) ? el_mul(sval[kk], x_at<false, T, Ti>(a.xv, scol[kk])) : el_zero(T());
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u)
+                if (k + u * G < e) acc = el_add(acc, p[u]);
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
+        }
+        if (valid && lane == 0) st_y(a.y + r0 + i, acc);
+    }
+    if (!values_in) mbar_wait(barB, 0);  // never leave with a copy in flight
+}
+
+// Tile headers of the direct row walk (class-1 tiles only): one warp per tile.
+template <class Ti>
+__global__ void __launch_bounds__(256) build_tile_headers_kernel(const Ti* __restrict__ rowptr, const TileDesc* __restrict__ tiles,
+                                                                 const unsigned char* __restrict__ cls, i64 ntiles, int window, int hdr_bytes,
+                                                                 unsigned char* __restrict__ hdrs) {
+    const i64 t = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= ntiles || cls[t] != 1) return;
+    unsigned char* h = hdrs + t * (i64)hdr_bytes;
+    const i64 r0 = tiles[t].row, r1 = tiles[t + 1].row, e = tiles[t + 1].nnz, w0 = t * (i64)window;
+    if (lane == 0) {
+        *reinterpret_cast<i64*>(h) = r0;
+        *reinterpret_cast<int*>(h + 8) = (int)(r1 - r0);
+        *reinterpret_cast<int*>(h + 12) = (int)(e - w0);
+    }
+    unsigned short* off = reinterpret_cast<unsigned short*>(h + 16);
+    for (i64 i = lane; i <= r1 - r0; i += 32) off[i] = (unsigned short)((i64)rowptr[r0 + i] - 1 - w0);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // very long rows ("merge-path split"): the row's nonzero range is cut into equal chunks, one CTA per chunk writes
 // one partial sum, a second kernel adds the partials of a row in chunk order.  Deterministic, no atomics.
 // ------------------------------------------------------------------------------------------------------------------
@@ -258,7 +414,8 @@ __global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ 
         const i64 o = __shfl_xor_sync(0xffffffffu, maxlen, m);
         maxlen = o > maxlen ? o : maxlen;
     }
-    const bool fits = (e - t * (i64)window) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap;  // staged from the window start
+    // staged from the window start; rp_cap - 8 rows is also what a tile header of the direct walk holds
+    const bool fits = (e - t * (i64)window) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap && (r1 - r0) <= (i64)(rp_cap - 8);
     const bool balanced = 2 * (e - s) >= (r1 - r0) * maxlen;
     if (lane == 0) cls[t] = (fits && balanced && e > s) ? 1 : 2;
 }
@@ -442,6 +599,7 @@ static TileShape shape_of(int itype, double avg_row, bool irregular, int lanes_o
         s.window = chunk - 64;
         s.cap = 0;
         s.rp_cap = 0;
+        s.ovf = s.hdr_rows = s.hdr_bytes = 0;
         s.general_elems = chunk + 512;
     } else {
         // measured on B200 (profiles/r1d_tune_*.txt): 27-point rows want ~70 KB tiles (G = 2: 128 rows, 3 CTAs per SM),
@@ -461,7 +619,14 @@ static TileShape shape_of(int itype, double avg_row, bool irregular, int lanes_o
         int slack = ((int)(4 * avg_row) + 31) & ~31;
         slack = slack < 64 ? 64 : slack > 512 ? 512 : slack;
         s.cap = s.window + slack;
-        s.rp_cap = (2 * (ROW_THREADS / G) + 8 + 3) & ~3;
+        // the direct walk over-fetches `ovf` entries past the window unconditionally (a typical last row never needs a
+        // second copy) and holds up to hdr_rows 16-bit row offsets per tile header
+        s.ovf = (((int)avg_row + 4) + 3) & ~3;
+        if (s.ovf > slack) s.ovf = slack;
+        s.hdr_rows = 2 * (ROW_THREADS / G);  // boundary rows of a stencil are shorter: up to twice the typical row count
+        if (s.cap > 65535) s.hdr_rows = 0;  // offsets would not fit 16 bits: no direct walk
+        s.hdr_bytes = (16 + 2 * (s.hdr_rows + 1) + 15) & ~15;
+        s.rp_cap = (s.hdr_rows + 8 + 3) & ~3;
         s.general_elems = s.cap + 256;
     }
     if (window_override >= 64 && irregular && window_override <= s.general_elems - 8) s.window = window_override & ~3;
@@ -552,6 +717,11 @@ static TileArgs<T, Ti> tile_args(const SpmvLaunch& L) {
     return a;
 }
 
+size_t direct_smem_bytes(int dtype, int itype, const TileShape& sh) {
+    const size_t ts = dtype == HPCLA_F32 ? 4 : dtype == HPCLA_F64 ? 8 : 16, is = itype == HPCLA_I32 ? 4 : 8;
+    return 16 + (size_t)sh.hdr_bytes + (size_t)sh.cap * (is + ts);
+}
+
 size_t rowwalk_smem_bytes(int dtype, int itype, const TileShape& sh) {
     const size_t ts = dtype == HPCLA_F32 ? 4 : dtype == HPCLA_F64 ? 8 : 16, is = itype == HPCLA_I32 ? 4 : 8;
     return 16 + is * (size_t)sh.rp_cap + (size_t)sh.cap * (is + ts);
@@ -586,6 +756,42 @@ static cudaError_t spmv_rowwalk_typed(const SpmvLaunch& L, cudaStream_t st) {
     return cudaErrorInvalidValue;
 }
 
+template <class T, class Ti, int G>
+static cudaError_t direct_launch(const SpmvLaunch& L, const DirectArgs<T, Ti>& a, size_t smem, cudaStream_t st) {
+    cudaError_t e;
+    if ((e = ensure_smem<spmv_rowwalk_direct_kernel<T, Ti, G>>(smem, true)) != cudaSuccess) return e;
+    spmv_rowwalk_direct_kernel<T, Ti, G><<<L.n_launch, ROW_THREADS, smem, st>>>(a, L.shape.cap);
+    return cudaGetLastError();
+}
+
+template <class T, class Ti>
+static cudaError_t spmv_direct_typed(const SpmvLaunch& L, cudaStream_t st) {
+    if (L.n_launch <= 0) return cudaSuccess;
+    DirectArgs<T, Ti> a;
+    a.colval = (const Ti*)L.colval;
+    a.nzval = (const T*)L.nzval;
+    a.hdrs = L.hdrs;
+    a.xv = make_xview<T>(L.x_own, L.gathered, L.own_lo, L.own_n);
+    a.y = (T*)L.y;
+    a.nnz_total = L.nnz;
+    a.runs.n = L.n_runs;
+    for (int j = 0; j < 8; ++j) a.runs.cta0[j] = L.run_cta0[j], a.runs.tile0[j] = L.run_tile0[j];
+    a.runs.cta0[8] = L.run_cta0[8];
+    a.window = L.shape.window;
+    a.ovf = L.shape.ovf;
+    a.hdr_bytes = L.shape.hdr_bytes;
+    const size_t smem = direct_smem_bytes(L.dtype, L.itype, L.shape);
+    switch (L.shape.lanes) {
+        case 1: return direct_launch<T, Ti, 1>(L, a, smem, st);
+        case 2: return direct_launch<T, Ti, 2>(L, a, smem, st);
+        case 4: return direct_launch<T, Ti, 4>(L, a, smem, st);
+        case 8: return direct_launch<T, Ti, 8>(L, a, smem, st);
+        case 16: return direct_launch<T, Ti, 16>(L, a, smem, st);
+        case 32: return direct_launch<T, Ti, 32>(L, a, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <class T, class Ti>
 static cudaError_t spmv_general_typed(const SpmvLaunch& L, cudaStream_t st) {
     if (L.n_launch <= 0) return cudaSuccess;
@@ -605,6 +811,16 @@ static cudaError_t spmv_general_typed(const SpmvLaunch& L, cudaStream_t st) {
 
 cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_rowwalk_typed, L, L, st); }
 cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_general_typed, L, L, st); }
+cudaError_t launch_spmv_direct(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_direct_typed, L, L, st); }
+
+cudaError_t launch_build_tile_headers(int itype, const void* rowptr, const TileDesc* tiles, const unsigned char* cls, i64 ntiles, int window, int hdr_bytes,
+                                      unsigned char* hdrs, cudaStream_t st) {
+    if (ntiles == 0) return cudaSuccess;
+    const int blocks = blocks_for(ntiles, 8);
+    if (itype == HPCLA_I32) build_tile_headers_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, tiles, cls, ntiles, window, hdr_bytes, hdrs);
+    else build_tile_headers_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, tiles, cls, ntiles, window, hdr_bytes, hdrs);
+    return cudaGetLastError();
+}
 
 template <class T, class Ti>
 static cudaError_t long_rows_typed(const LongRowsLaunch& L, cudaStream_t st) {

@@ -1,0 +1,1 @@
+for w in poisson256 poisson256-i64 stencil27 stencil27-f64 laplace2d; do timeout 300 python tools/tune_spmv.py --workload $w --no-direct 2>&1 | grep -v Warn; done | tee gpurun_out/r14_tune_direct.log

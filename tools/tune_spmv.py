@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--kinds", default="", help="comma list of HPCLA_SPMV_KIND values (general, rowwalk)")
     ap.add_argument("--lanes", default="", help="comma list of HPCLA_LANES values")
     ap.add_argument("--sweep", default="", help="comma list of lanes:window pairs")
+    ap.add_argument("--no-direct", action="store_true", help="also time HPCLA_DIRECT=0 (the record-driven row walk)")
     ap.add_argument("--cusparse", action="store_true")
     ap.add_argument("--n", type=int, default=20_000_000, help="rows of the power-law matrix")
     args = ap.parse_args()
@@ -98,6 +99,8 @@ def main():
         configs.append({"HPCLA_LANES": int(g), "HPCLA_TILE_WINDOW": int(w)})
     for w in [int(v) for v in args.windows.split(",") if v]:
         configs.append({"HPCLA_TILE_WINDOW": w})
+    if args.no_direct:
+        configs.append({"HPCLA_DIRECT": 0})
 
     ref = None
     for env in configs:
