@@ -160,7 +160,6 @@ struct hpcla_spmv {
     i64 *d_local_src = nullptr, *d_local_dst = nullptr;     // only when needed (fallback / gather hook)
     TileRec* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
     int n_list[2][2] = {{0, 0}, {0, 0}};
-    i64 list_tile0[2][2] = {{-1, -1}, {-1, -1}};  // first tile of a list of consecutive tiles, else -1
     std::vector<int> h_list[2][2];  // host copies (block boundaries of the staged multiply)
     struct HostPipe* pipe = nullptr;
     cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
@@ -555,7 +554,6 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
             for (int g = 0; g < 2; ++g) {
                 op->n_list[c][g] = (int)lists[c][g].size();
                 if (lists[c][g].empty()) continue;
-                if ((i64)lists[c][g].back() - (i64)lists[c][g].front() + 1 == (i64)lists[c][g].size()) op->list_tile0[c][g] = lists[c][g].front();
                 std::vector<TileRec> recs(lists[c][g].size());
                 for (size_t q = 0; q < recs.size(); ++q) {
                     const TileDesc &t0 = A->h_tiles[(size_t)lists[c][g][q]], &t1 = A->h_tiles[(size_t)lists[c][g][q] + 1];
@@ -730,10 +728,12 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
     L.hdrs = A->d_hdrs;
 }
 
-// Positions [lo, hi) of an ascending tile list as at most 8 runs of consecutive tiles (the direct row walk's launch
-// description).  False when the slice is more fragmented than that.
-static bool direct_runs(const std::vector<int>& list, int lo, int hi, SpmvLaunch& L) {
+// Positions [lo, hi) of an ascending tile list as at most 8 runs of consecutive tiles (what lets a CTA find its window
+// by arithmetic).  False (n_runs = 0) when the slice is more fragmented than that.
+template <class Launch>
+static bool tile_runs(const std::vector<int>& list, int lo, int hi, Launch& L) {
     int n = 0;
+    L.n_runs = 0;
     for (int q = lo; q < hi;) {
         if (n == 8) return false;
         int q1 = q + 1;
@@ -755,10 +755,10 @@ static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t s
     for (int c = 0; c < 2; ++c) {
         const int lo = from ? from[c] : 0, hi = to ? to[c] : op->n_list[c][which];
         L.recs = op->d_list[c][which] + lo;
-        L.tile0 = op->list_tile0[c][which] >= 0 ? op->list_tile0[c][which] + lo : -1;
         L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
-        if (c == 0 && !L.has_ghost && op->csr->d_hdrs && direct_runs(op->h_list[0][which], lo, hi, L)) CU_TRY(launch_spmv_direct(L, stream));
+        const bool runs = tile_runs(op->h_list[c][which], lo, hi, L);
+        if (c == 0 && runs && !L.has_ghost && op->csr->d_hdrs) CU_TRY(launch_spmv_direct(L, stream));
         else if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
         else CU_TRY(launch_spmv_general(L, stream));
         op->launches += 1;
@@ -940,9 +940,9 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
         L.kn = op->mm_ncols - k0 >= 4 ? 4 : 1;
         for (int c = 0; c < 2; ++c) {
             L.recs = op->d_list[c][which];
-            L.tile0 = op->list_tile0[c][which];
             L.n_launch = op->n_list[c][which];
             if (L.n_launch <= 0) continue;
+            tile_runs(op->h_list[c][which], 0, L.n_launch, L);
             if (c == 0 && walk) CU_TRY(launch_spmm_rowwalk(L, stream));
             else CU_TRY(launch_spmm_rows(L, stream));
             op->launches += 1;

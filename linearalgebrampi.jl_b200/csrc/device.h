@@ -43,9 +43,8 @@ struct SpmvLaunch {
     i64 nrows, nnz;
     TileShape shape;        // as fixed when the tile table was built
     const TileRec* recs;    // [n_launch] the tiles of this launch, one CTA each
-    i64 tile0 = -1;         // >= 0: recs are the consecutive tiles tile0, tile0 + 1, ...
-    // direct row walk: the launch as <= 8 runs of consecutive tiles (run j = CTAs run_cta0[j] .. run_cta0[j+1]-1)
-    const unsigned char* hdrs = nullptr;
+    // the launch as <= 8 runs of consecutive tiles (run j = CTAs run_cta0[j] .. run_cta0[j+1]-1); n_runs = 0: none
+    const unsigned char* hdrs = nullptr;  // direct row walk: tile headers
     int n_runs = 0;
     int run_cta0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int run_tile0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -91,7 +90,9 @@ struct SpmmLaunch {
     i64 nrows, nnz;
     TileShape shape;
     const TileRec* recs;
-    i64 tile0 = -1;
+    int n_runs = 0;
+    int run_cta0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int run_tile0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int n_launch;
     const void* b_own;  // B's local block, column-major, at the first own source row (column 0)
     i64 ldb;

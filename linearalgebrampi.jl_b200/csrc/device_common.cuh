@@ -153,6 +153,31 @@ __device__ __forceinline__ T x_at(const XView<T>& xv, Ti c) {
     return ld_x(xv.own + (i64)c);
 }
 
+// A launch over an ascending tile list, described by value as at most 8 runs of consecutive tiles: the CTA's tile, hence
+// its window of the nonzero stream, is then arithmetic on kernel parameters (no load in front of the first copy).
+struct TileRuns {
+    int n;         // runs in use (<= 8); 0: no such description, the tile records say everything
+    int cta0[9];   // run j covers CTAs cta0[j] .. cta0[j+1]-1
+    int tile0[8];  // first tile of run j
+};
+__device__ __forceinline__ i64 tile_of_cta(const TileRuns& runs) {
+    // constant indices only after unrolling: the arrays stay in the parameter bank / registers (a run-time index would
+    // put a by-value copy of them on the local-memory stack)
+    const int cta = (int)blockIdx.x;
+    int tile = runs.tile0[0] + (cta - runs.cta0[0]);
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+        if (j < runs.n && cta >= runs.cta0[j]) tile = runs.tile0[j] + (cta - runs.cta0[j]);
+    return (i64)tile;
+}
+static inline TileRuns launch_runs(int n, const int* cta0, const int* tile0) {
+    TileRuns r;
+    r.n = n;
+    for (int j = 0; j < 8; ++j) r.cta0[j] = cta0[j], r.tile0[j] = tile0[j];
+    r.cta0[8] = cta0[8];
+    return r;
+}
+
 template <class T, class Ti>
 struct TileArgs {
     const Ti* rowptr;
@@ -161,7 +186,7 @@ struct TileArgs {
     XView<T> xv;
     T* y;
     const TileRec* recs;  // one record per CTA of this launch
-    i64 tile0;            // >= 0: the launch covers the consecutive tiles tile0, tile0 + 1, ... (window arithmetic)
+    TileRuns runs;        // n > 0: the launch as runs of consecutive tiles (window arithmetic)
     int window;           // stored entries per tile window
     i64 nnz_total;
     i64 long_threshold;
@@ -277,7 +302,7 @@ struct StageArgs {
     const Ti* colval;
     const T* nzval;
     const TileRec* recs;  // one record per CTA of this launch
-    i64 tile0;            // >= 0: the launch covers the consecutive tiles tile0, tile0 + 1, ... (window arithmetic)
+    TileRuns runs;        // n > 0: the launch as runs of consecutive tiles (window arithmetic)
     int window;           // stored entries per tile window
     i64 nnz_total;
 };
@@ -298,13 +323,13 @@ __device__ __forceinline__ Staged<T, Ti> stage_tile(const StageArgs<T, Ti>& a, i
     Ti* scol = srp + rp_cap;
     T* sval = reinterpret_cast<T*>(scol + cap);
     const int tid = threadIdx.x;
-    // A launch over consecutive tiles knows where its window of the nonzero stream starts without reading anything:
+    // A launch described as runs of consecutive tiles knows where its window of the nonzero stream starts without reading anything:
     // the bulk copies of the window are issued first, the tile record (rows, exact end) is fetched while they fly.
-    const bool contig = a.tile0 >= 0;
+    const bool contig = a.runs.n > 0;
     i64 w0 = 0;
     int n_main = 0;
     if (contig) {
-        w0 = (a.tile0 + (i64)blockIdx.x) * (i64)a.window;
+        w0 = tile_of_cta(a.runs) * (i64)a.window;
         const i64 left = (a.nnz_total - w0) & ~(i64)3;
         n_main = (int)(left < (i64)a.window ? (left > 0 ? left : 0) : (i64)a.window);
     }
@@ -356,7 +381,7 @@ __device__ __forceinline__ Staged<T, Ti> stage_tile(const StageArgs<T, Ti>& a, i
 
 template <class T, class Ti>
 __device__ __forceinline__ StageArgs<T, Ti> stage_args(const TileArgs<T, Ti>& a) {
-    return StageArgs<T, Ti>{a.rowptr, a.colval, a.nzval, a.recs, a.tile0, a.window, a.nnz_total};
+    return StageArgs<T, Ti>{a.rowptr, a.colval, a.nzval, a.recs, a.runs, a.window, a.nnz_total};
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -139,12 +139,6 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - (GHOST ? 1 : 0)
 // gathers; those fly while the values are still landing; when B lands only shared-memory reads and the arithmetic are
 // left.  The (rare) rows that overrun the unconditional over-fetch get a second, conditional copy.
 // ------------------------------------------------------------------------------------------------------------------
-struct TileRuns {
-    int n;         // runs in use (<= 8)
-    int cta0[9];   // run j covers CTAs cta0[j] .. cta0[j+1]-1
-    int tile0[8];  // first tile of run j
-};
-
 template <class T, class Ti>
 struct DirectArgs {
     const Ti* colval;
@@ -172,12 +166,7 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - HPCLA_DIRECT_CT
     Ti* scol = reinterpret_cast<Ti*>(smem_raw + 16 + a.hdr_bytes);
     T* sval = reinterpret_cast<T*>(scol + cap);
     const int tid = threadIdx.x;
-    // my tile: a short compare chain over kernel parameters
-    int run = 0;
-#pragma unroll
-    for (int j = 1; j < 8; ++j)
-        if (j < a.runs.n && (int)blockIdx.x >= a.runs.cta0[j]) run = j;
-    const i64 tile = (i64)a.runs.tile0[run] + ((int)blockIdx.x - a.runs.cta0[run]);
+    const i64 tile = tile_of_cta(a.runs);
     const i64 w0 = tile * (i64)a.window;
     const i64 left = (a.nnz_total - w0) & ~(i64)3;
     const int want = a.window + a.ovf;
@@ -709,7 +698,7 @@ static TileArgs<T, Ti> tile_args(const SpmvLaunch& L) {
     a.xv = make_xview<T>(L.x_own, L.gathered, L.own_lo, L.own_n);
     a.y = (T*)L.y;
     a.recs = L.recs;
-    a.tile0 = L.tile0;
+    a.runs = launch_runs(L.n_runs, L.run_cta0, L.run_tile0);
     a.window = L.shape.window;
     a.nnz_total = L.nnz;
     a.long_threshold = L.long_threshold;
@@ -774,9 +763,7 @@ static cudaError_t spmv_direct_typed(const SpmvLaunch& L, cudaStream_t st) {
     a.xv = make_xview<T>(L.x_own, L.gathered, L.own_lo, L.own_n);
     a.y = (T*)L.y;
     a.nnz_total = L.nnz;
-    a.runs.n = L.n_runs;
-    for (int j = 0; j < 8; ++j) a.runs.cta0[j] = L.run_cta0[j], a.runs.tile0[j] = L.run_tile0[j];
-    a.runs.cta0[8] = L.run_cta0[8];
+    a.runs = launch_runs(L.n_runs, L.run_cta0, L.run_tile0);
     a.window = L.shape.window;
     a.ovf = L.shape.ovf;
     a.hdr_bytes = L.shape.hdr_bytes;

@@ -135,7 +135,7 @@ __global__ void pack_rows_kernel(const T* __restrict__ B, i64 ldb, const i64* __
 template <class T, class Ti>
 static TileArgsM<T, Ti> tile_args_m(const SpmmLaunch& L) {
     TileArgsM<T, Ti> a;
-    a.st = StageArgs<T, Ti>{(const Ti*)L.rowptr, (const Ti*)L.colval, (const T*)L.nzval, L.recs, L.tile0, L.shape.window, L.nnz};
+    a.st = StageArgs<T, Ti>{(const Ti*)L.rowptr, (const Ti*)L.colval, (const T*)L.nzval, L.recs, launch_runs(L.n_runs, L.run_cta0, L.run_tile0), L.shape.window, L.nnz};
     a.xv.own = L.b_own ? (const T*)L.b_own - L.own_lo : nullptr;
     a.xv.ghost = (const T*)L.ghost;
     a.xv.ldb = L.ldb;
