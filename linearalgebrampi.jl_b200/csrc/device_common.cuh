@@ -127,7 +127,13 @@ __device__ __forceinline__ void st_y(cplx* p, cplx v) { __stcs(reinterpret_cast<
 
 // general kernel, per element type: CTA size and 4-nonzero groups per lane and round
 template <class T> struct TileCfg;
-template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = 2; };
+#ifndef HPCLA_GENERAL_F32_GROUPS
+#define HPCLA_GENERAL_F32_GROUPS 2  // A/B knob
+#endif
+#ifndef HPCLA_GENERAL_MIN_CTAS
+#define HPCLA_GENERAL_MIN_CTAS 1  // A/B knob: resident CTAs per SM the general kernel's registers are allocated for
+#endif
+template <> struct TileCfg<float> { static constexpr int THREADS = 256, GROUPS = HPCLA_GENERAL_F32_GROUPS; };
 template <> struct TileCfg<double> { static constexpr int THREADS = 256, GROUPS = 2; };
 template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 1; };
 // row-walk kernel: CTA size, and the resident CTAs per SM the register allocation aims at

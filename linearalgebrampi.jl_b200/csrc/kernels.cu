@@ -41,7 +41,7 @@ __device__ __forceinline__ void reduce_rows(const T* prod, const Ti* __restrict_
 }
 
 template <class T, class Ti, int THREADS, int GROUPS, bool GHOST>
-__global__ void __launch_bounds__(THREADS) spmv_tile_kernel(const TileArgs<T, Ti> a, int smem_elems) {
+__global__ void __launch_bounds__(THREADS, HPCLA_GENERAL_MIN_CTAS) spmv_tile_kernel(const TileArgs<T, Ti> a, int smem_elems) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* prod = reinterpret_cast<T*>(smem_raw);
     constexpr int CHUNK = THREADS * GROUPS * 4;
