@@ -39,6 +39,7 @@ typedef struct hpcla_planb hpcla_planb; /* VectorPlan under construction (betwee
 typedef struct hpcla_plan hpcla_plan;   /* index fields of a VectorPlan (src/vectors.jl:229-251)                   */
 typedef struct hpcla_spmv hpcla_spmv;   /* (csr, plan) bound to device buffers: what `A*x` / `mul!` execute         */
 typedef struct hpcla_tb hpcla_tb;       /* TransposePlan under construction / its result (src/sparse.jl:1519-1538) */
+typedef struct hpcla_dtb hpcla_dtb;     /* the same result, built and held on the device                          */
 
 int hpcla_abi_version(void);
 const char* hpcla_last_error(void);
@@ -114,6 +115,24 @@ int hpcla_transpose_finish(hpcla_tb* tb, const int64_t* recv_counts, const int64
                            const void* const* recv_vals, int64_t* nrows_out, int64_t* nnz_out, int64_t* ncc_out);
 int hpcla_tb_result(const hpcla_tb* tb, void* rowptr_out, void* colval_out, int64_t* col_indices_out, void* nzval_out);
 void hpcla_tb_destroy(hpcla_tb* tb);
+
+/* The same materialisation entirely on the device: TransposePlan(A) + execute_plan!(plan, A) —
+ * src/sparse.jl:1551-1744, 1756-1829 — without the host copies, the host-staged tag-10/tag-11 messages and the host
+ * tuple sort (:1655).  Inputs are A's device arrays as for hpcla_csr_create plus its host partitions and col_indices.
+ * Every local nonzero is keyed (row of A^T local to its owner, global column of A^T), dropped into its owner's send
+ * range, exchanged with grouped ncclSend/ncclRecv, radix-sorted (CUB), and turned into CSR with compressed columns.
+ * Collective (NCCL world or nranks == 1).  Results are bit-identical to hpcla_transpose_begin/finish.
+ *   sizes  = rows (of A^T owned here), stored entries, compressed columns
+ *   result = device-to-device copies into caller-owned arrays (rowptr Ti[nrows+1], colval Ti[nnz], nzval T[nnz]) and
+ *            col_indices (Int64[ncc]) to the host; blocks until done. */
+int hpcla_transpose_device(hpcla_ctx* ctx, int dtype, int itype, const int64_t* row_partition,
+                           const int64_t* col_partition, int64_t nrows_local, int64_t ncols_compressed, int64_t nnz,
+                           const void* d_rowptr, const void* d_colval, const int64_t* h_col_indices,
+                           const void* d_nzval, void* stream, hpcla_dtb** out);
+int hpcla_dtb_sizes(const hpcla_dtb* t, int64_t* nrows_out, int64_t* nnz_out, int64_t* ncc_out);
+int hpcla_dtb_result(const hpcla_dtb* t, void* d_rowptr_out, void* d_colval_out, int64_t* h_col_indices_out,
+                     void* d_nzval_out, void* stream);
+void hpcla_dtb_destroy(hpcla_dtb* t);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Device objects.

@@ -70,6 +70,10 @@ SIGNATURES = {
     "hpcla_transpose_finish": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_tb_result": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hpcla_tb_destroy": (None, [_vp]),
+    "hpcla_transpose_device": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hpcla_dtb_sizes": (_i, [_vp, _vp, _vp, _vp]),
+    "hpcla_dtb_result": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "hpcla_dtb_destroy": (None, [_vp]),
     "hpcla_csr_create": (_i, [_vp, _i, _i, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "hpcla_csr_info": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_csr_tile_classes": (_i, [_vp, _vp, _vp, _vp, _vp]),

@@ -298,6 +298,37 @@ extern "C" void hpcla_ctx_destroy(hpcla_ctx* ctx) {
     delete ctx;
 }
 
+namespace hpcla {
+int ctx_rank_info(const hpcla_ctx* ctx, int* device, int* rank, int* nranks, int* has_comm) {
+    if (!ctx) return fail(HPCLA_ERR_ARG, "ctx_rank_info: null");
+    *device = ctx->device;
+    *rank = ctx->rank;
+    *nranks = ctx->nranks;
+    *has_comm = ctx->comm ? 1 : 0;
+    return HPCLA_OK;
+}
+
+int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, const i64* send_bytes, void* d_recv, const i64* recv_off,
+                       const i64* recv_bytes, cudaStream_t stream) {
+    if (!ctx) return fail(HPCLA_ERR_ARG, "ctx_exchange_bytes: null");
+    const int me = ctx->rank;
+    if (send_bytes[me] != recv_bytes[me]) return fail(HPCLA_ERR_STATE, "ctx_exchange_bytes: own range sizes differ");
+    if (send_bytes[me] > 0)
+        CU_TRY(cudaMemcpyAsync((char*)d_recv + recv_off[me], (const char*)d_send + send_off[me], (size_t)send_bytes[me], cudaMemcpyDeviceToDevice, stream));
+    if (ctx->nranks == 1) return HPCLA_OK;
+    if (!ctx->comm) return fail(HPCLA_ERR_STATE, "ctx_exchange_bytes: no NCCL communicator");
+    NcclApi* api = nccl_api();
+    NCCL_TRY(api->GroupStart());
+    for (int q = 0; q < ctx->nranks; ++q) {
+        if (q == me) continue;
+        if (send_bytes[q] > 0) NCCL_TRY(api->Send((const char*)d_send + send_off[q], (size_t)send_bytes[q], ncclChar, q, ctx->comm, stream));
+        if (recv_bytes[q] > 0) NCCL_TRY(api->Recv((char*)d_recv + recv_off[q], (size_t)recv_bytes[q], ncclChar, q, ctx->comm, stream));
+    }
+    NCCL_TRY(api->GroupEnd());
+    return HPCLA_OK;
+}
+}  // namespace hpcla
+
 // ---------------------------------------------------------------------------------------------------------------
 // CSR view
 // ---------------------------------------------------------------------------------------------------------------

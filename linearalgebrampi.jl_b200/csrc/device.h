@@ -127,6 +127,12 @@ struct LongRowsLaunch {
 };
 cudaError_t launch_long_rows(const LongRowsLaunch& L, cudaStream_t st);
 
+// context.cu, for the other translation units: who am I, and an all-to-all of byte ranges between device buffers
+// (grouped ncclSend/ncclRecv; the range for my own rank is a device-to-device copy).  NCCL world or nranks == 1.
+int ctx_rank_info(const hpcla_ctx* ctx, int* device, int* rank, int* nranks, int* has_comm);
+int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, const i64* send_bytes, void* d_recv, const i64* recv_off,
+                       const i64* recv_bytes, cudaStream_t stream);
+
 // out[k] = x[idx[k]-1]          (pack of src/vectors.jl:431-437, all peers in one launch)
 cudaError_t launch_pack(int dtype, const void* x, const i64* idx, i64 n, void* out, cudaStream_t st);
 // gathered[dst[k]-1] = x[src[k]-1]   (local copy of src/vectors.jl:426-428 == _gather_kernel! :174-177)

@@ -18,6 +18,7 @@ backends.py (the reference does it with MPI at the same places).
 from __future__ import annotations
 
 import ctypes
+import os
 import itertools
 from typing import Dict, List, Optional, Tuple
 
@@ -490,6 +491,11 @@ def materialize_transpose(A: HPCSparseMatrix) -> HPCSparseMatrix:
     b = A.backend
     comm = b.comm
     rank, P = comm_rank(comm), comm_size(comm)
+    if b.is_cuda and os.environ.get("HPCLA_TRANSPOSE", "device") != "host" and (P == 1 or b.ctx().world == "nccl"):
+        Y = _materialize_transpose_device(A)
+        A.cached_transpose = Y
+        Y.cached_transpose = A
+        return Y
     nz = np.ascontiguousarray(A.nzval_host())  # _ensure_cpu(A.nzval) (:1760)
     tb = ctypes.c_void_p()
     _lib.check(L.hpcla_transpose_begin(rank, P, _lib.dtype_code(b.T), _lib.itype_code(b.Ti), _lib.ptr(A.row_partition), _lib.ptr(A.col_partition),
@@ -528,6 +534,36 @@ def materialize_transpose(A: HPCSparseMatrix) -> HPCSparseMatrix:
     A.cached_transpose = Y  # :1858-1859
     Y.cached_transpose = A
     return Y
+
+
+def _materialize_transpose_device(A: HPCSparseMatrix) -> HPCSparseMatrix:
+    """The same result without leaving the GPU (hpcla_transpose_device): keys built on the device,
+    exchanged over NCCL, radix-sorted, turned into CSR.  The host copies of rowptr / colval the structure-side code
+    expects (plans, hashes) are read back once."""
+    import torch
+
+    L = _lib.lib()
+    b = A.backend
+    h = ctypes.c_void_p()
+    ci = np.ascontiguousarray(A.col_indices, dtype=np.int64)
+    stream = _current_stream(b)
+    _lib.check(L.hpcla_transpose_device(b.ctx().handle, _lib.dtype_code(b.T), _lib.itype_code(b.Ti), _lib.ptr(A.row_partition), _lib.ptr(A.col_partition),
+                                        A.nrows_local, A.ncols_compressed, A.nnz_local, _lib.ptr(A.rowptr_target), _lib.ptr(A.colval_target), _lib.ptr(ci),
+                                        _lib.ptr(A.nzval), stream, ctypes.byref(h)))
+    try:
+        nrows, nnz, ncc = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(L.hpcla_dtb_sizes(h, ctypes.byref(nrows), ctypes.byref(nnz), ctypes.byref(ncc)))
+        dev = b.torch_device()
+        ti = torch.int32 if np.dtype(b.Ti) == np.int32 else torch.int64
+        rowptr_d = torch.empty(nrows.value + 1, dtype=ti, device=dev)
+        colval_d = torch.empty(nnz.value, dtype=ti, device=dev)
+        nzval_d = torch.empty(nnz.value, dtype=_torch_dtype(b.T), device=dev)
+        col_indices = np.empty(ncc.value, dtype=np.int64)
+        _lib.check(L.hpcla_dtb_result(h, _lib.ptr(rowptr_d), _lib.ptr(colval_d), _lib.ptr(col_indices), _lib.ptr(nzval_d), stream))
+    finally:
+        L.hpcla_dtb_destroy(h)
+    return HPCSparseMatrix(None, A.col_partition.copy(), A.row_partition.copy(), col_indices, rowptr_d.cpu().numpy(), colval_d.cpu().numpy(), nzval_d,
+                           int(nrows.value), int(ncc.value), rowptr_d, colval_d, b)
 
 
 def transpose_matvec(A: HPCSparseMatrix, x: HPCVector) -> HPCVector:

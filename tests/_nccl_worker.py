@@ -62,6 +62,10 @@ def main():
         Cg = C.to_global()
         assert relerr(Cg, orc.matmat(olocs, Bg)) <= TOL[np.dtype(T)], ("A*B", kind)
         assert np.array_equal(Cg[:, 0], y.to_global()), ("A*B column 0 vs A*x", kind)
+        # device-side transpose over NCCL: this rank's block of A^T, array by array, against the oracle's TransposePlan
+        At, ot = la.materialize_transpose(A), orc.transpose(olocs)[rank]
+        assert np.array_equal(At.rowptr, ot.rowptr) and np.array_equal(At.colval, ot.colval) and np.array_equal(At.col_indices, ot.col_indices)
+        assert np.array_equal(At.nzval_host(), ot.nzval), ("transpose values", kind)
         W = orc.PlanWorld(olocs, orc.uniform_partition(n, P))
         assert np.array_equal(g.cpu().numpy(), W.execute(orc.split_vector(xh, orc.uniform_partition(n, P)))[rank])
         W.close()

@@ -470,3 +470,32 @@ def test_repartition_and_mismatched_partitions(T, P):
         assert np.array_equal(yg, v)
         assert abs(d - np.vdot(v, w)) <= (1e-3 if T == np.float32 else 1e-10) * n
         assert relerr(zg, 2 * v + w) <= TOL[np.dtype(T)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device-side transpose: same arrays as the host builder and the oracle, bit for bit
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,Ti", [(np.float64, np.int32), (np.complex128, np.int64), (np.float32, np.int32)])
+def test_device_transpose_matches_host_builder(T, Ti, monkeypatch):
+    rng = np.random.default_rng(77)
+    S = la.synth
+    b = la.backend_cuda_serial(T, Ti)
+    mats = [_ragged(rng, 400, 300, 0.03, T, long_rows=((7, 250),)), _ragged(rng, 50, 2000, 0.01, T), sp.csr_matrix((5, 9), dtype=T)]
+    rp, c, v = S.stencil_local(2, 12, 0, 12**3, T, Ti)
+    mats.append(sp.csr_matrix((v, c - 1, rp - 1), shape=(12**3, 12**3)))
+    for M in mats:
+        monkeypatch.setenv("HPCLA_TRANSPOSE", "device")
+        A = la.HPCSparseMatrix.from_global(M, b)
+        Yd = la.materialize_transpose(A)
+        monkeypatch.setenv("HPCLA_TRANSPOSE", "host")
+        A2 = la.HPCSparseMatrix.from_global(M, b)
+        Yh = la.materialize_transpose(A2)
+        assert Yd is not Yh and Yd.nrows_local == Yh.nrows_local and Yd.ncols_compressed == Yh.ncols_compressed
+        for name in ("rowptr", "colval", "col_indices"):
+            assert np.array_equal(getattr(Yd, name), getattr(Yh, name)), name
+        assert np.array_equal(Yd.nzval_host(), Yh.nzval_host())
+        assert np.array_equal(Yd.rowptr_target.cpu().numpy(), Yh.rowptr) and np.array_equal(Yd.colval_target.cpu().numpy(), Yh.colval)
+        ref = sp.csr_matrix(M.T)
+        ref.sort_indices()
+        assert np.array_equal(Yd.rowptr - 1, ref.indptr) and np.array_equal(Yd.col_indices[Yd.colval - 1] - 1, ref.indices)
+        assert la.materialize_transpose(A) is Yd and la.materialize_transpose(Yd) is A  # cached both ways (src/sparse.jl:1858-1859)
