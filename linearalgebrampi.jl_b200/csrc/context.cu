@@ -161,6 +161,8 @@ struct hpcla_spmv {
     TileRec* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
     int n_list[2][2] = {{0, 0}, {0, 0}};
     std::vector<int> h_list[2][2];  // host copies (block boundaries of the staged multiply)
+    // every list as runs of consecutive tiles, found once: {first position in the list, first tile}, ascending
+    std::vector<std::pair<int, int>> runs[2][2];
     struct HostPipe* pipe = nullptr;
     cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
     bool halo_recorded = false;
@@ -585,6 +587,8 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
             for (int g = 0; g < 2; ++g) {
                 op->n_list[c][g] = (int)lists[c][g].size();
                 if (lists[c][g].empty()) continue;
+                for (size_t q = 0; q < lists[c][g].size(); ++q)
+                    if (q == 0 || lists[c][g][q] != lists[c][g][q - 1] + 1) op->runs[c][g].push_back({(int)q, lists[c][g][q]});
                 std::vector<TileRec> recs(lists[c][g].size());
                 for (size_t q = 0; q < recs.size(); ++q) {
                     const TileDesc &t0 = A->h_tiles[(size_t)lists[c][g][q]], &t1 = A->h_tiles[(size_t)lists[c][g][q] + 1];
@@ -762,20 +766,24 @@ static void fill_launch(const hpcla_spmv* op, SpmvLaunch& L, const void* d_x, vo
 // Positions [lo, hi) of an ascending tile list as at most 8 runs of consecutive tiles (what lets a CTA find its window
 // by arithmetic).  False (n_runs = 0) when the slice is more fragmented than that.
 template <class Launch>
-static bool tile_runs(const std::vector<int>& list, int lo, int hi, Launch& L) {
-    int n = 0;
+static bool tile_runs(const std::vector<std::pair<int, int>>& runs, int lo, int hi, Launch& L) {
     L.n_runs = 0;
-    for (int q = lo; q < hi;) {
-        if (n == 8) return false;
-        int q1 = q + 1;
-        while (q1 < hi && list[(size_t)q1] == list[(size_t)q1 - 1] + 1) ++q1;
-        L.run_cta0[n] = q - lo;
-        L.run_tile0[n] = list[(size_t)q];
+    if (hi <= lo || runs.empty()) return false;
+    // the run holding position lo: last run starting at or before it
+    size_t j = (size_t)(std::upper_bound(runs.begin(), runs.end(), std::make_pair(lo, INT32_MAX)) - runs.begin()) - 1;
+    int n = 0;
+    for (; j < runs.size() && runs[j].first < hi; ++j) {
+        if (n == 8) {
+            L.n_runs = 0;
+            return false;
+        }
+        const int start = std::max(runs[j].first, lo);
+        L.run_cta0[n] = start - lo;
+        L.run_tile0[n] = runs[j].second + (start - runs[j].first);
         ++n;
-        q = q1;
     }
-    for (int j = n; j <= 8; ++j) L.run_cta0[j] = hi - lo;
-    for (int j = n; j < 8; ++j) L.run_tile0[j] = 0;
+    for (int k = n; k <= 8; ++k) L.run_cta0[k] = hi - lo;
+    for (int k = n; k < 8; ++k) L.run_tile0[k] = 0;
     L.n_runs = n;
     return n > 0;
 }
@@ -788,7 +796,7 @@ static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t s
         L.recs = op->d_list[c][which] + lo;
         L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
-        const bool runs = tile_runs(op->h_list[c][which], lo, hi, L);
+        const bool runs = tile_runs(op->runs[c][which], lo, hi, L);
         if (c == 0 && runs && !L.has_ghost && op->csr->d_hdrs) CU_TRY(launch_spmv_direct(L, stream));
         else if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
         else CU_TRY(launch_spmv_general(L, stream));
@@ -973,7 +981,7 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
             L.recs = op->d_list[c][which];
             L.n_launch = op->n_list[c][which];
             if (L.n_launch <= 0) continue;
-            tile_runs(op->h_list[c][which], 0, L.n_launch, L);
+            tile_runs(op->runs[c][which], 0, L.n_launch, L);
             if (c == 0 && walk) CU_TRY(launch_spmm_rowwalk(L, stream));
             else CU_TRY(launch_spmm_rows(L, stream));
             op->launches += 1;

@@ -163,24 +163,27 @@ __device__ __forceinline__ T x_at(const XView<T>& xv, Ti c) {
 // its window of the nonzero stream, is then arithmetic on kernel parameters (no load in front of the first copy).
 struct TileRuns {
     int n;         // runs in use (<= 8); 0: no such description, the tile records say everything
-    int cta0[9];   // run j covers CTAs cta0[j] .. cta0[j+1]-1
-    int tile0[8];  // first tile of run j
+    int cta0[8];   // run j starts at CTA cta0[j] (ascending; unused runs: INT_MAX, so they never match)
+    int skip[8];   // tile - CTA index within run j (= first tile of the run - cta0[j])
 };
 __device__ __forceinline__ i64 tile_of_cta(const TileRuns& runs) {
-    // constant indices only after unrolling: the arrays stay in the parameter bank / registers (a run-time index would
-    // put a by-value copy of them on the local-memory stack)
+    // Constant indices only after unrolling (a run-time index would put a by-value copy of the arrays on the local-memory
+    // stack), and no load depends on a comparison: the 16 parameter loads go out together, then 7 selects.
     const int cta = (int)blockIdx.x;
-    int tile = runs.tile0[0] + (cta - runs.cta0[0]);
+    int skip = runs.skip[0];
+    if (runs.n > 1) {  // uniform: a single run (the common case) needs one parameter
 #pragma unroll
-    for (int j = 1; j < 8; ++j)
-        if (j < runs.n && cta >= runs.cta0[j]) tile = runs.tile0[j] + (cta - runs.cta0[j]);
-    return (i64)tile;
+        for (int j = 1; j < 8; ++j) skip = (cta >= runs.cta0[j]) ? runs.skip[j] : skip;
+    }
+    return (i64)(cta + skip);
 }
 static inline TileRuns launch_runs(int n, const int* cta0, const int* tile0) {
     TileRuns r;
     r.n = n;
-    for (int j = 0; j < 8; ++j) r.cta0[j] = cta0[j], r.tile0[j] = tile0[j];
-    r.cta0[8] = cta0[8];
+    for (int j = 0; j < 8; ++j) {
+        r.cta0[j] = j < n ? cta0[j] : 0x7fffffff;
+        r.skip[j] = j < n ? tile0[j] - cta0[j] : 0;
+    }
     return r;
 }
 

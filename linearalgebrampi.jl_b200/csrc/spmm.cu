@@ -43,12 +43,21 @@ struct TileArgsM {
     int k0;   // first column of this launch
 };
 
+// Registers: left to itself ptxas squeezes this kernel into 32 registers (8 CTAs per SM) and, depending on a handful of
+// live values, pays for it by reusing one destination register for all gathers of a batch, i.e. by serialising them
+// (measured: 495 -> 601 us per 4 columns).  The bound below gives it room for the whole batch in flight.
+#ifndef HPCLA_SPMM_MIN_CTAS
+#define HPCLA_SPMM_MIN_CTAS 6  // A/B knob
+#endif
 template <class T, class Ti, int G, bool GHOST, int K>
-__global__ void __launch_bounds__(ROW_THREADS) spmm_rowwalk_kernel(const TileArgsM<T, Ti> a, int cap, int rp_cap, i64 rowptr_len) {
+__global__ void __launch_bounds__(ROW_THREADS, HPCLA_SPMM_MIN_CTAS) spmm_rowwalk_kernel(const TileArgsM<T, Ti> a, int cap, int rp_cap, i64 rowptr_len) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Staged<T, Ti> st = stage_tile<T, Ti>(a.st, cap, rp_cap, rowptr_len, smem_raw);
     constexpr int RPP = ROW_THREADS / G;
-    constexpr int EB = K >= 4 ? 2 : 4;  // entries per batch: EB * K gathers in flight per lane
+#ifndef HPCLA_SPMM_EB4
+#define HPCLA_SPMM_EB4 2  // A/B knob: entries per batch at K = 4
+#endif
+    constexpr int EB = K >= 4 ? HPCLA_SPMM_EB4 : 4;  // entries per batch: EB * K gathers in flight per lane
     const int tid = threadIdx.x, lane = tid % G;
     for (i64 base = st.r0; base < st.r1; base += RPP) {
         const i64 r = base + tid / G;
