@@ -139,7 +139,10 @@ template <> struct TileCfg<cplx> { static constexpr int THREADS = 256, GROUPS = 
 // row-walk kernel: CTA size, and the resident CTAs per SM the register allocation aims at
 constexpr int ROW_THREADS = 256;
 template <class T> struct RowCfg { static constexpr int CTAS = 8; };   // 32 registers per thread
-template <> struct RowCfg<double> { static constexpr int CTAS = 7; };  // 36
+#ifndef HPCLA_F64_CTAS
+#define HPCLA_F64_CTAS 7  // A/B knob
+#endif
+template <> struct RowCfg<double> { static constexpr int CTAS = HPCLA_F64_CTAS; };  // 7: 36 registers
 template <> struct RowCfg<cplx> { static constexpr int CTAS = HPCLA_CPLX_CTAS; };  // 48 (16-byte values)
 
 // x addressing: own columns are read straight from x.v (no local copy into `gathered`), ghosts from `gathered`.
