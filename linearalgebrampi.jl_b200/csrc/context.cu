@@ -33,6 +33,7 @@ struct NcclApi {
     void* handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;  // optional
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -60,6 +61,7 @@ NcclApi* nccl_api() {
     if (!api.field) api.error = std::string("libnccl lacks ") + sym;
         LOAD(GetUniqueId, "ncclGetUniqueId")
         LOAD(CommInitRank, "ncclCommInitRank")
+        api.CommInitRankConfig = (decltype(api.CommInitRankConfig))dlsym(api.handle, "ncclCommInitRankConfig");
         LOAD(CommDestroy, "ncclCommDestroy")
         LOAD(Send, "ncclSend")
         LOAD(Recv, "ncclRecv")
@@ -184,6 +186,21 @@ struct hpcla_spmv {
     i64 launches = 0;
 };
 
+// Handles under construction: destroyed on every early return, released on success.
+template <class H, void (*Destroy)(H*)>
+struct Building {
+    H* h;
+    explicit Building(H* p) : h(p) {}
+    ~Building() {
+        if (h) Destroy(h);
+    }
+    H* release() {
+        H* p = h;
+        h = nullptr;
+        return p;
+    }
+};
+
 static int set_device(const hpcla_ctx* ctx) {
     CU_TRY(cudaSetDevice(ctx->device));
     return HPCLA_OK;
@@ -237,7 +254,18 @@ extern "C" int hpcla_ctx_init_nccl(hpcla_ctx* ctx, const void* id128) {
     if (rc) return rc;
     ncclUniqueId id;
     std::memcpy(&id, id128, 128);
-    NCCL_TRY(api->CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank));
+    // The halo messages are a few MB at most: a communicator capped at a few CTAs leaves the SMs to the multiply
+    // (HPCLA_NCCL_MAX_CTAS, tuning hook; unset = NCCL's default).
+    int max_ctas = 0;
+    if (const char* e = getenv("HPCLA_NCCL_MAX_CTAS")) max_ctas = atoi(e);
+    if (max_ctas > 0 && api->CommInitRankConfig) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = max_ctas;
+        NCCL_TRY(api->CommInitRankConfig(&ctx->comm, ctx->nranks, id, ctx->rank, &cfg));
+    } else {
+        NCCL_TRY(api->CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank));
+    }
     ctx->comm_owned = true;
     return HPCLA_OK;
 }
@@ -345,6 +373,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     int rc = set_device(ctx);
     if (rc) return rc;
     hpcla_csr* A = new hpcla_csr();
+    Building<hpcla_csr, hpcla_csr_destroy> guard(A);
     A->ctx = ctx;
     A->dtype = dtype;
     A->itype = itype;
@@ -384,10 +413,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         const bool irregular = (pass == 1) || kind == 2;
         A->shape = tile_shape(dtype, itype, avg_row, irregular, lanes_override, window_override);
         A->ntiles = nnz / A->shape.window + 1;
-        if (A->ntiles >= (i64)INT32_MAX) {
-            delete A;
-            return fail(HPCLA_ERR_ARG, "hpcla_csr_create: too many tiles");
-        }
+        if (A->ntiles >= (i64)INT32_MAX) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: too many tiles");
         if (A->d_tiles) cudaFree(A->d_tiles);
         A->d_tiles = nullptr;
         CU_TRY(cudaMalloc(&A->d_tiles, sizeof(TileDesc) * (size_t)(A->ntiles + 1)));
@@ -459,7 +485,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         CU_TRY(cudaMemcpy(A->d_chunk_ptr, chunk_ptr.data(), sizeof(i64) * chunk_ptr.size(), cudaMemcpyHostToDevice));
     }
     cudaFree(d_rows);
-    *out = A;
+    *out = guard.release();
     return HPCLA_OK;
 }
 
@@ -510,6 +536,7 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
     if (rc) return rc;
     const size_t es = dtype_size(A->dtype);
     hpcla_spmv* op = new hpcla_spmv();
+    Building<hpcla_spmv, hpcla_spmv_destroy> guard(op);
     op->ctx = ctx;
     op->csr = A;
     op->plan = *plan;
@@ -517,18 +544,18 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
     const hpcla_plan& P = op->plan;
     // validate what the kernels rely on
     for (i64 v : P.local_src)
-        if (v < 1 || v > n_x_local) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: local_src index out of range"); }
+        if (v < 1 || v > n_x_local) { return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: local_src index out of range"); }
     for (auto& s : P.send_indices)
         for (i64 v : s)
-            if (v < 1 || v > n_x_local) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: send index out of range"); }
-    if (!is_consecutive(P.local_dst)) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: local_dst_indices must be a consecutive range (col_indices sorted, contiguous partition)"); }
+            if (v < 1 || v > n_x_local) { return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: send index out of range"); }
+    if (!is_consecutive(P.local_dst)) { return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: local_dst_indices must be a consecutive range (col_indices sorted, contiguous partition)"); }
     for (auto& s : P.recv_perm)
-        if (s.empty() || !is_consecutive(s)) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: every recv_perm must be a non-empty consecutive range"); }
+        if (s.empty() || !is_consecutive(s)) { return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: every recv_perm must be a non-empty consecutive range"); }
     // every position of gathered must be produced exactly once
     {
         i64 covered = (i64)P.local_dst.size();
         for (auto& s : P.recv_perm) covered += (i64)s.size();
-        if (covered != P.n_gathered) { delete op; return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: plan covers %lld of %lld gathered positions", (long long)covered, (long long)P.n_gathered); }
+        if (covered != P.n_gathered) { return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: plan covers %lld of %lld gathered positions", (long long)covered, (long long)P.n_gathered); }
     }
     op->own_n = (i64)P.local_dst.size();
     op->own_lo = op->own_n ? P.local_dst[0] : 1;
@@ -536,7 +563,7 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
     op->x_in_place = is_consecutive(P.local_src);
     op->has_ghost = !P.recv_perm.empty();
     op->has_peers = !P.recv_rank_ids.empty() || !P.send_rank_ids.empty();
-    if (op->has_peers && !ctx->comm && !ctx->group && ctx->nranks > 1) { delete op; return fail(HPCLA_ERR_STATE, "hpcla_spmv_create: the plan exchanges data but the context has neither an NCCL communicator nor a single-process group"); }
+    if (op->has_peers && !ctx->comm && !ctx->group && ctx->nranks > 1) { return fail(HPCLA_ERR_STATE, "hpcla_spmv_create: the plan exchanges data but the context has neither an NCCL communicator nor a single-process group"); }
     for (size_t i = 0; i < P.recv_rank_ids.size(); ++i) op->recvs.push_back(Seg{(int)P.recv_rank_ids[i], P.recv_perm[i][0], (i64)P.recv_perm[i].size(), true, 0});
     i64 off = 0;
     for (size_t i = 0; i < P.send_rank_ids.size(); ++i) {
@@ -605,7 +632,7 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
         if ((i64)g->ops.size() <= op->seq) g->ops.resize((size_t)op->seq + 1, std::vector<hpcla_spmv*>(g->ctxs.size(), nullptr));
         g->ops[(size_t)op->seq][(size_t)ctx->rank] = op;
     }
-    *out = op;
+    *out = guard.release();
     return HPCLA_OK;
 }
 
@@ -626,7 +653,7 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
     if (op->ctx->group) {
         hpcla_group* g = op->ctx->group;
         std::lock_guard<std::mutex> lk(g->mu);
-        if ((i64)g->ops.size() > op->seq) g->ops[(size_t)op->seq][(size_t)op->ctx->rank] = nullptr;
+        if ((i64)g->ops.size() > op->seq && g->ops[(size_t)op->seq][(size_t)op->ctx->rank] == op) g->ops[(size_t)op->seq][(size_t)op->ctx->rank] = nullptr;
     }
     cudaFree(op->d_gathered);
     cudaFree(op->d_ghost_rm);
@@ -1403,6 +1430,10 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     char* q = p + (size_t)n * es;
     double* d_s = nullptr;  // rr_k at [2k], pq at the tail
     CU_TRY(cudaMalloc(&d_s, sizeof(double) * (size_t)(2 * (iters + 1) + 2)));
+    struct FreeOnExit {
+        double* p;
+        ~FreeOnExit() { cudaFree(p); }
+    } free_d_s{d_s};
     double* d_pq = d_s + 2 * (iters + 1);
     const bool multi = ctx->comm && ctx->nranks > 1;
     NcclApi* api = multi ? nccl_api() : nullptr;
@@ -1411,7 +1442,7 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     if (multi) NCCL_TRY(api->AllReduce(d_s, d_s, 1, ncclFloat64, ncclSum, ctx->comm, stream));
     for (int k = 0; k < iters; ++k) {
         rc = hpcla_spmv_run(op, p, q, stream);
-        if (rc) { cudaFree(d_s); return rc; }
+        if (rc) return rc;
         CU_TRY(launch_dot(dtype, n, p, q, ctx->d_red_scratch, d_pq, stream));
         if (multi) NCCL_TRY(api->AllReduce(d_pq, d_pq, 1, ncclFloat64, ncclSum, ctx->comm, stream));
         CU_TRY(launch_cg_update_xr(dtype, n, p, q, d_x, r, d_s + 2 * k, d_pq, ctx->d_red_scratch, d_s + 2 * (k + 1), stream));
@@ -1422,7 +1453,6 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     std::vector<double> h((size_t)(2 * (iters + 1)));
     CU_TRY(cudaMemcpyAsync(h.data(), d_s, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream));
     CU_TRY(cudaStreamSynchronize(stream));
-    cudaFree(d_s);
     if (rr_history_out)
         for (int k = 0; k < iters; ++k) rr_history_out[k] = h[(size_t)(2 * (k + 1))];
     return HPCLA_OK;
