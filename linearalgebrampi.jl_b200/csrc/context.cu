@@ -166,6 +166,9 @@ struct hpcla_spmv {
     // every list as runs of consecutive tiles, found once: {first position in the list, first tile}, ascending
     std::vector<std::pair<int, int>> runs[2][2];
     struct HostPipe* pipe = nullptr;
+    // fused dot(x, A x) for CG: one partial per row-walk CTA, interior list first, then boundary list
+    double* d_dot_partials = nullptr;
+    bool dot_request = false;
     cudaEvent_t ev_x = nullptr, ev_packed = nullptr, ev_halo = nullptr;
     bool halo_recorded = false;
     // in-flight call
@@ -664,6 +667,7 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
     cudaFree(op->d_local_dst);
     for (int c = 0; c < 2; ++c)
         for (int g = 0; g < 2; ++g) cudaFree(op->d_list[c][g]);
+    cudaFree(op->d_dot_partials);
     if (op->pipe) {
         for (cudaEvent_t e : op->pipe->ev_in) cudaEventDestroy(e);
         for (cudaEvent_t e : op->pipe->ev_c) cudaEventDestroy(e);
@@ -824,7 +828,12 @@ static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t s
         L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
         const bool runs = tile_runs(op->runs[c][which], lo, hi, L);
-        if (c == 0 && runs && !L.has_ghost && op->csr->d_hdrs) CU_TRY(launch_spmv_direct(L, stream));
+        L.dot_x = nullptr;
+        if (c == 0 && op->dot_request) {  // whole lists only (hpcla_cg): partials of the interior list, then the boundary list
+            L.dot_x = op->cur_x;
+            L.dot_out = op->d_dot_partials + (which == 1 ? op->n_list[0][0] : 0);
+        }
+        if (c == 0 && runs && !L.has_ghost && op->csr->d_hdrs && !op->dot_request) CU_TRY(launch_spmv_direct(L, stream));
         else if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
         else CU_TRY(launch_spmv_general(L, stream));
         op->launches += 1;
@@ -1440,10 +1449,19 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     CU_TRY(launch_cg_init(dtype, n, d_b, d_x, r, p, ctx->d_red_scratch, d_s, stream));
     op->launches += 1;
     if (multi) NCCL_TRY(api->AllReduce(d_s, d_s, 1, ncclFloat64, ncclSum, ctx->comm, stream));
+    // p.q rides on the multiply when every row goes through the row-walk kernel (stencil-like matrices): the multiply
+    // leaves one partial per CTA, a one-CTA kernel adds them in a fixed order — p and q are not read a second time
+    const i64 n_partials = (i64)op->n_list[0][0] + op->n_list[0][1];
+    const bool fused = op->n_list[1][0] + op->n_list[1][1] == 0 && op->csr->nlong == 0 && op->x_in_place && op->own_src0 == 1 && n_partials > 0 &&
+                       !getenv("HPCLA_CG_UNFUSED");
+    if (fused && !op->d_dot_partials) CU_TRY(cudaMalloc(&op->d_dot_partials, sizeof(double) * (size_t)n_partials));
     for (int k = 0; k < iters; ++k) {
+        op->dot_request = fused;
         rc = hpcla_spmv_run(op, p, q, stream);
+        op->dot_request = false;
         if (rc) return rc;
-        CU_TRY(launch_dot(dtype, n, p, q, ctx->d_red_scratch, d_pq, stream));
+        if (fused) CU_TRY(launch_dot_partials_sum(op->d_dot_partials, n_partials, d_pq, stream));
+        else CU_TRY(launch_dot(dtype, n, p, q, ctx->d_red_scratch, d_pq, stream));
         if (multi) NCCL_TRY(api->AllReduce(d_pq, d_pq, 1, ncclFloat64, ncclSum, ctx->comm, stream));
         CU_TRY(launch_cg_update_xr(dtype, n, p, q, d_x, r, d_s + 2 * k, d_pq, ctx->d_red_scratch, d_s + 2 * (k + 1), stream));
         if (multi) NCCL_TRY(api->AllReduce(d_s + 2 * (k + 1), d_s + 2 * (k + 1), 1, ncclFloat64, ncclSum, ctx->comm, stream));

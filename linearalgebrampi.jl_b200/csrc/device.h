@@ -58,6 +58,9 @@ struct SpmvLaunch {
     bool has_ghost;  // false: every column is own (single rank, or no off-rank columns)
     void* y;
     i64 long_threshold;  // rows longer than this are left to the split kernels
+    // row-walk kernel only: also produce dot(dot_x, y) as one double partial per CTA (dot_x[r] pairs with local row r)
+    const void* dot_x = nullptr;
+    double* dot_out = nullptr;
 };
 
 cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles,
@@ -77,6 +80,8 @@ cudaError_t launch_classify_tiles(int itype, const void* colval, const TileDesc*
 cudaError_t launch_tile_maxcol(int itype, const void* colval, const TileDesc* tiles, i64 ntiles, i64 own_lo, i64 own_n, i64* out, cudaStream_t st);
 cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 1
 cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st);  // tiles of class 2
+// out2[0] = sum of the n per-CTA partials of a fused dot, in a fixed order; out2[1] = 0
+cudaError_t launch_dot_partials_sum(const double* partials, i64 n, double* out2, cudaStream_t st);
 cudaError_t launch_spmv_direct(const SpmvLaunch& L, cudaStream_t st);   // tiles of class 1, ghost-free, as runs of consecutive tiles
 cudaError_t launch_build_tile_headers(int itype, const void* rowptr, const TileDesc* tiles, const unsigned char* cls, i64 ntiles, int window, int hdr_bytes,
                                       unsigned char* hdrs, cudaStream_t st);

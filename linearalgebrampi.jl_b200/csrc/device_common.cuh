@@ -203,6 +203,9 @@ struct TileArgs {
     i64 nnz_total;
     i64 long_threshold;
     i64 safe_col;  // a column that is always valid to read (padding lanes)
+    // fused dot(x, A x) of the row-walk kernel (CG's p.q): dot_x[r] pairs with row r; one partial per CTA (double)
+    const T* dot_x;
+    double* dot_out;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -261,11 +264,18 @@ __device__ __forceinline__ T block_sum(T v, T* sh /* [32] */) {
 // Row walk: G lanes per row (interleaved: lane g takes entries g, g+G, ...), operands read from shared memory, x
 // gathered per entry.  Lanes of a warp own consecutive rows, so on banded matrices the gathers of one warp instruction
 // fall into a few contiguous runs (coalesced).  G = 1 sums left to right: the reference's order, bit for bit.
-template <class T, class Ti, int THREADS, int G, bool GHOST>
-__device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const Ti* rp, i64 rp_off, const XView<T>& xv, T* __restrict__ y, i64 r0,
-                                          i64 r1, i64 s4, int tid) {
+__device__ __forceinline__ double dot_term(float x, float y) { return (double)x * (double)y; }
+__device__ __forceinline__ double dot_term(double x, double y) { return x * y; }
+__device__ __forceinline__ double dot_term(cplx, cplx) { return 0.0; }  // the fused dot is for real types (CG)
+
+// Returns this thread's share of sum_r dot_x[r] * y[r] over the rows it stored (0 when dot_x is null).
+// DOT is a template parameter: the plain multiply must not carry the dot's live registers through its gather loop.
+template <class T, class Ti, int THREADS, int G, bool GHOST, bool DOT = false>
+__device__ __forceinline__ double rows_walk(const Ti* scol, const T* sval, const Ti* rp, i64 rp_off, const XView<T>& xv, T* __restrict__ y, i64 r0,
+                                            i64 r1, i64 s4, int tid, const T* __restrict__ dot_x = nullptr) {
     constexpr int RPP = THREADS / G;
     const int lane = tid % G;
+    double dot = 0.0;
     for (i64 base = r0; base < r1; base += RPP) {
         const i64 r = base + tid / G;
         const bool valid = r < r1;
@@ -302,8 +312,12 @@ __device__ __forceinline__ void rows_walk(const Ti* scol, const T* sval, const T
 #pragma unroll
             for (int m = G / 2; m >= 1; m >>= 1) acc = el_add(acc, shfl_xor(acc, m));
         }
-        if (valid && lane == 0) st_y(y + r, acc);
+        if (valid && lane == 0) {
+            st_y(y + r, acc);
+            if (DOT) dot += dot_term(ld_x(dot_x + r), acc);
+        }
     }
+    return dot;
 }
 
 // The matrix side of a tile, shared by the multiply kernels: what the bulk copies need (StageArgs), what they leave in

@@ -13,6 +13,8 @@
 // The reference's 1-based Int32/Int64 arrays are consumed as they are (no conversion pass, no private copy).
 // With one lane per row the sum runs left to right over products rounded separately from the adds, i.e. it is
 // bit-identical to the reference's `acc += nzval[j]*x[colval[j]]` (no FMA contraction).
+#include <type_traits>
+
 #include "device_common.cuh"
 
 namespace hpcla {
@@ -122,12 +124,43 @@ __global__ void __launch_bounds__(THREADS, HPCLA_GENERAL_MIN_CTAS) spmv_tile_ker
     }
 }
 
-template <class T, class Ti, int G, bool GHOST>
+template <class T, class Ti, int G, bool GHOST, bool DOT = false>
 __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS - (GHOST ? 1 : 0))
     spmv_rowwalk_kernel(const TileArgs<T, Ti> a, int cap, int rp_cap, i64 rowptr_len) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Staged<T, Ti> st = stage_tile<T, Ti>(stage_args(a), cap, rp_cap, rowptr_len, smem_raw);
-    rows_walk<T, Ti, ROW_THREADS, G, GHOST>(st.scol, st.sval, st.srp, st.rp0, a.xv, a.y, st.r0, st.r1, st.s4, (int)threadIdx.x);
+    const double dot = rows_walk<T, Ti, ROW_THREADS, G, GHOST, DOT>(st.scol, st.sval, st.srp, st.rp0, a.xv, a.y, st.r0, st.r1, st.s4, (int)threadIdx.x, a.dot_x);
+    if (DOT) {  // CG's p.q rides on the multiply; one partial per CTA, summed in a fixed order later
+        __shared__ double dsh[ROW_THREADS / 32];
+        double v = dot;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if ((threadIdx.x & 31) == 0) dsh[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < ROW_THREADS / 32; ++w) t += dsh[w];
+            a.dot_out[blockIdx.x] = t;
+        }
+    }
+}
+
+// out2[0] = sum of n per-CTA partials, fixed order (thread t takes t, t + 1024, ...; then a fixed tree); out2[1] = 0
+__global__ void __launch_bounds__(1024) dot_partials_sum_kernel(const double* __restrict__ partials, i64 n, double* __restrict__ out2) {
+    __shared__ double sh[32];
+    double v = 0.0;
+    for (i64 i = threadIdx.x; i < n; i += 1024) v += partials[i];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = sh[threadIdx.x];
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (threadIdx.x == 0) out2[0] = v, out2[1] = 0.0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -703,6 +736,8 @@ static TileArgs<T, Ti> tile_args(const SpmvLaunch& L) {
     a.nnz_total = L.nnz;
     a.long_threshold = L.long_threshold;
     a.safe_col = L.own_n > 0 ? L.own_lo : 1;
+    a.dot_x = (const T*)L.dot_x;
+    a.dot_out = L.dot_out;
     return a;
 }
 
@@ -719,6 +754,18 @@ size_t rowwalk_smem_bytes(int dtype, int itype, const TileShape& sh) {
 template <class T, class Ti, int G>
 static cudaError_t rowwalk_launch(const SpmvLaunch& L, const TileArgs<T, Ti>& a, size_t smem, cudaStream_t st) {
     cudaError_t e;
+    if constexpr (!std::is_same<T, cplx>::value) {
+        if (L.dot_x) {  // the instantiations that also leave dot(dot_x, y) partials (real types: CG)
+            if (L.has_ghost) {
+                if ((e = ensure_smem<spmv_rowwalk_kernel<T, Ti, G, true, true>>(smem, true)) != cudaSuccess) return e;
+                spmv_rowwalk_kernel<T, Ti, G, true, true><<<L.n_launch, ROW_THREADS, smem, st>>>(a, L.shape.cap, L.shape.rp_cap, L.nrows + 1);
+            } else {
+                if ((e = ensure_smem<spmv_rowwalk_kernel<T, Ti, G, false, true>>(smem, true)) != cudaSuccess) return e;
+                spmv_rowwalk_kernel<T, Ti, G, false, true><<<L.n_launch, ROW_THREADS, smem, st>>>(a, L.shape.cap, L.shape.rp_cap, L.nrows + 1);
+            }
+            return cudaGetLastError();
+        }
+    }
     if (L.has_ghost) {
         if ((e = ensure_smem<spmv_rowwalk_kernel<T, Ti, G, true>>(smem, true)) != cudaSuccess) return e;
         spmv_rowwalk_kernel<T, Ti, G, true><<<L.n_launch, ROW_THREADS, smem, st>>>(a, L.shape.cap, L.shape.rp_cap, L.nrows + 1);
@@ -797,6 +844,10 @@ static cudaError_t spmv_general_typed(const SpmvLaunch& L, cudaStream_t st) {
 }
 
 cudaError_t launch_spmv_rowwalk(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_rowwalk_typed, L, L, st); }
+cudaError_t launch_dot_partials_sum(const double* partials, i64 n, double* out2, cudaStream_t st) {
+    dot_partials_sum_kernel<<<1, 1024, 0, st>>>(partials, n, out2);
+    return cudaGetLastError();
+}
 cudaError_t launch_spmv_general(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_general_typed, L, L, st); }
 cudaError_t launch_spmv_direct(const SpmvLaunch& L, cudaStream_t st) { HPCLA_DISPATCH(spmv_direct_typed, L, L, st); }
 

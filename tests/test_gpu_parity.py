@@ -499,3 +499,36 @@ def test_device_transpose_matches_host_builder(T, Ti, monkeypatch):
         ref.sort_indices()
         assert np.array_equal(Yd.rowptr - 1, ref.indptr) and np.array_equal(Yd.col_indices[Yd.colval - 1] - 1, ref.indices)
         assert la.materialize_transpose(A) is Yd and la.materialize_transpose(Yd) is A  # cached both ways (src/sparse.jl:1858-1859)
+
+
+@pytest.mark.parametrize("Ti", [np.int32, np.int64])
+def test_cg_fused_dot_matches_unfused(Ti, monkeypatch):
+    """hpcla_cg lets p.q ride on the multiply (one partial per row-walk CTA) for stencil-like matrices; the residual
+    history agrees with the separate dot kernel and with the oracle's textbook CG.  Int64 indices exercise the switch
+    away from the direct row walk while the dot is requested; a ragged matrix (general tiles) keeps the separate dot."""
+    T = np.float64
+    b = la.backend_cuda_serial(T, Ti)
+    N = 20
+    n = N**3
+    A = la.synth.stencil_matrix(1, N, b)
+    rp, c, v = la.synth.stencil_local(1, N, 0, n, T, Ti)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    bvec = (G @ np.ones(n)).astype(T)
+    bv = la.HPCVector.from_global(bvec, b)
+    sol_f, hist_f = la.cg(A, bv, 30)
+    monkeypatch.setenv("HPCLA_CG_UNFUSED", "1")
+    sol_u, hist_u = la.cg(A, bv, 30)
+    monkeypatch.delenv("HPCLA_CG_UNFUSED")
+    xo, ho = orc.cg(orc.distribute(G, 1, itype="i32" if Ti == np.int32 else "i64"), bvec, 30)
+    assert np.allclose(hist_f, hist_u, rtol=1e-9) and np.allclose(hist_f, ho, rtol=1e-8)
+    assert relerr(sol_f.to_global(), xo) <= 1e-9 and relerr(sol_u.to_global(), xo) <= 1e-9
+    # a matrix with general tiles: SPD by construction, the separate dot kernel runs
+    rng = np.random.default_rng(3)
+    R = _ragged(rng, 600, 600, 0.02, T, long_rows=((11, 400),))
+    S = sp.csr_matrix(R @ R.T + sp.identity(600) * 5.0)
+    S.sort_indices()
+    As = la.HPCSparseMatrix.from_global(S, b)
+    bs = rng.uniform(-1, 1, 600)
+    sol, hist = la.cg(As, la.HPCVector.from_global(bs, b), 20)
+    xo, ho = orc.cg(orc.distribute(S, 1, itype="i32" if Ti == np.int32 else "i64"), bs, 20)
+    assert relerr(sol.to_global(), xo) <= 1e-6 and np.allclose(hist, ho, rtol=1e-5, atol=1e-10 * ho[0])  # the tail is rounding noise
