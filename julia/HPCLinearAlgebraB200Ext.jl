@@ -146,6 +146,67 @@ function mul_staged!(y_host::Vector{T}, y::HPCVector{T,B}, A::HPCSparseMatrix{T,
     return y_host
 end
 
+# --- A * B::HPCMatrix: replaces the column-by-column loop of src/sparse.jl:2391-2413 (ncols SpMVs, each with a column
+#     extraction and its own ghost exchange) by one exchange for all columns and tiles staged once per 4 columns.
+function Base.:*(A::HPCSparseMatrix{T,Ti,B}, Bm::HPCMatrix{T,B}) where {T,Ti,B<:CuB}
+    ncols = size(Bm, 2)
+    col1 = HPCVector_local(view(Bm.A, :, 1), A.backend)               # a column's partition = B's row partition (src/indexing.jl:385-393)
+    plan = get_vector_plan(A, col1)
+    b = _bind(A, col1, plan)
+    C = CUDA.zeros(T, A.nrows_local, ncols)                           # column-major, like B.A
+    GC.@preserve Bm C begin
+        status = @ccall libhpcla.hpcla_spmm_run(b.op::Ptr{Cvoid}, _dptr(Bm.A)::Ptr{Cvoid}, Int64(stride(Bm.A, 2))::Int64, _dptr(C)::Ptr{Cvoid},
+                                                Int64(max(A.nrows_local, 1))::Int64, Cint(ncols)::Cint, _stream()::Ptr{Cvoid})::Cint
+        if status == 4   # HPCLA_ERR_STATE: own columns not contiguous in B's rows on some rank -> the reference's loop (all ranks agree:
+            return invoke(Base.:*, Tuple{HPCSparseMatrix{T,Ti},HPCMatrix{T}}, A, Bm)   # decide it once, collectively, as the Python mirror does)
+        end
+        _check(status, "hpcla_spmm_run")
+    end
+    return HPCMatrix_local(C, A.backend)
+end
+
+# --- repartition(x, p): replaces VectorRepartitionPlan + execute_plan! (src/vectors.jl:519-676: host-staged, tag 92) ------------
+function HPCLinearAlgebra.repartition(x::HPCVector{T,B}, p::Vector{Int}) where {T,B<:CuB}
+    (x.partition === p || x.partition == p) && return x              # the reference's fast path (src/vectors.jl:714-716)
+    nr = length(p) - 1
+    rank = comm_rank(x.backend.comm)
+    ns = Ref{Int64}(0); nrv = Ref{Int64}(0); sz = Ref{Int64}(0)
+    s1 = zeros(Int64, nr); s2 = zeros(Int64, nr); s3 = zeros(Int64, nr)
+    r1 = zeros(Int64, nr); r2 = zeros(Int64, nr); r3 = zeros(Int64, nr); loc = zeros(Int64, 3)
+    _check(@ccall(libhpcla.hpcla_repartition_plan(Cint(rank)::Cint, Cint(nr)::Cint, x.partition::Ptr{Int64}, p::Ptr{Int64}, ns::Ptr{Int64}, s1::Ptr{Int64},
+              s2::Ptr{Int64}, s3::Ptr{Int64}, nrv::Ptr{Int64}, r1::Ptr{Int64}, r2::Ptr{Int64}, r3::Ptr{Int64}, loc::Ptr{Int64}, sz::Ptr{Int64})::Cint),
+           "hpcla_repartition_plan")
+    out = CUDA.zeros(T, sz[])
+    GC.@preserve x out begin
+        _check(@ccall(libhpcla.hpcla_repartition_run(_context(x.backend)::Ptr{Cvoid}, _dtype(T)::Cint, ns[]::Int64, s1::Ptr{Int64}, s2::Ptr{Int64}, s3::Ptr{Int64},
+                  nrv[]::Int64, r1::Ptr{Int64}, r2::Ptr{Int64}, r3::Ptr{Int64}, loc::Ptr{Int64}, _dptr(x.v)::Ptr{Cvoid}, _dptr(out)::Ptr{Cvoid},
+                  _stream()::Ptr{Cvoid})::Cint), "hpcla_repartition_run")
+    end
+    return HPCVector{T,B}(compute_partition_hash(p), copy(p), out, x.backend)
+end
+
+# --- HPCSparseMatrix(transpose(A)): replaces TransposePlan + execute_plan! (src/sparse.jl:1551-1829) and keeps the
+#     bidirectional cache of src/sparse.jl:1846-1865
+function HPCLinearAlgebra.HPCSparseMatrix(At::Transpose{T,<:HPCSparseMatrix{T,Ti,B}}) where {T,Ti,B<:CuB}
+    A = At.parent
+    A.cached_transpose !== nothing && return A.cached_transpose
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(@ccall(libhpcla.hpcla_transpose_device(_context(A.backend)::Ptr{Cvoid}, _dtype(T)::Cint, _itype(Ti)::Cint, A.row_partition::Ptr{Int64},
+              A.col_partition::Ptr{Int64}, Int64(A.nrows_local)::Int64, Int64(A.ncols_compressed)::Int64, Int64(length(A.nzval))::Int64,
+              _dptr(A.rowptr_target)::Ptr{Cvoid}, _dptr(A.colval_target)::Ptr{Cvoid}, A.col_indices::Ptr{Int64}, _dptr(A.nzval)::Ptr{Cvoid},
+              _stream()::Ptr{Cvoid}, h::Ptr{Ptr{Cvoid}})::Cint), "hpcla_transpose_device")
+    nrows = Ref{Int64}(0); nnz = Ref{Int64}(0); ncc = Ref{Int64}(0)
+    _check(@ccall(libhpcla.hpcla_dtb_sizes(h[]::Ptr{Cvoid}, nrows::Ptr{Int64}, nnz::Ptr{Int64}, ncc::Ptr{Int64})::Cint), "hpcla_dtb_sizes")
+    rowptr_d = CUDA.zeros(Ti, nrows[] + 1); colval_d = CUDA.zeros(Ti, nnz[]); nzval_d = CUDA.zeros(T, nnz[]); col_indices = zeros(Int, ncc[])
+    _check(@ccall(libhpcla.hpcla_dtb_result(h[]::Ptr{Cvoid}, _dptr(rowptr_d)::Ptr{Cvoid}, _dptr(colval_d)::Ptr{Cvoid}, col_indices::Ptr{Int64},
+              _dptr(nzval_d)::Ptr{Cvoid}, _stream()::Ptr{Cvoid})::Cint), "hpcla_dtb_result")
+    @ccall libhpcla.hpcla_dtb_destroy(h[]::Ptr{Cvoid})::Cvoid
+    Y = HPCSparseMatrix{T,Ti,B}(nothing, copy(A.col_partition), copy(A.row_partition), col_indices, Array(rowptr_d), Array(colval_d), nzval_d,
+                                Int(nrows[]), Int(ncc[]), nothing, nothing, rowptr_d, colval_d, A.backend)   # field order: src/sparse.jl:319-337
+    A.cached_transpose = Y; Y.cached_transpose = A
+    return Y
+end
+
 # --- transpose(A) * x: src/sparse.jl:2375-2379 already materialises and caches A^T and calls A_transposed * x, which
 #     now dispatches to the method above; nothing to override.  (The one-time TransposePlan stays the reference's.)
 
