@@ -50,14 +50,14 @@ struct TileArgsM {
 #define HPCLA_SPMM_MIN_CTAS 6  // A/B knob
 #endif
 template <class T, class Ti, int G, bool GHOST, int K>
-__global__ void __launch_bounds__(ROW_THREADS, HPCLA_SPMM_MIN_CTAS) spmm_rowwalk_kernel(const TileArgsM<T, Ti> a, int cap, int rp_cap, i64 rowptr_len) {
+__global__ void __launch_bounds__(ROW_THREADS, K >= 8 ? 4 : HPCLA_SPMM_MIN_CTAS) spmm_rowwalk_kernel(const TileArgsM<T, Ti> a, int cap, int rp_cap, i64 rowptr_len) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Staged<T, Ti> st = stage_tile<T, Ti>(a.st, cap, rp_cap, rowptr_len, smem_raw);
     constexpr int RPP = ROW_THREADS / G;
 #ifndef HPCLA_SPMM_EB4
 #define HPCLA_SPMM_EB4 2  // A/B knob: entries per batch at K = 4
 #endif
-    constexpr int EB = K >= 4 ? HPCLA_SPMM_EB4 : 4;  // entries per batch: EB * K gathers in flight per lane
+    constexpr int EB = K >= 8 ? 1 : K >= 4 ? HPCLA_SPMM_EB4 : 4;  // entries per batch: EB * K gathers in flight per lane
     const int tid = threadIdx.x, lane = tid % G;
     for (i64 base = st.r0; base < st.r1; base += RPP) {
         const i64 r = base + tid / G;
@@ -186,6 +186,7 @@ static cudaError_t spmm_rowwalk_lanes(const SpmmLaunch& L, cudaStream_t st) {
 template <class T, class Ti>
 static cudaError_t spmm_rowwalk_typed(const SpmmLaunch& L, cudaStream_t st) {
     if (L.n_launch <= 0) return cudaSuccess;
+    if (L.kn == 8) return spmm_rowwalk_lanes<T, Ti, 8>(L, st);
     if (L.kn == 4) return spmm_rowwalk_lanes<T, Ti, 4>(L, st);
     if (L.kn == 1) return spmm_rowwalk_lanes<T, Ti, 1>(L, st);
     return cudaErrorInvalidValue;
@@ -195,7 +196,10 @@ template <class T, class Ti>
 static cudaError_t spmm_rows_typed(const SpmmLaunch& L, cudaStream_t st) {
     if (L.n_launch <= 0) return cudaSuccess;
     const TileArgsM<T, Ti> a = tile_args_m<T, Ti>(L);
-    if (L.kn == 4) {
+    if (L.kn == 8) {
+        if (L.has_ghost) spmm_rows_warp_kernel<T, Ti, true, 8><<<L.n_launch, 256, 0, st>>>(a);
+        else spmm_rows_warp_kernel<T, Ti, false, 8><<<L.n_launch, 256, 0, st>>>(a);
+    } else if (L.kn == 4) {
         if (L.has_ghost) spmm_rows_warp_kernel<T, Ti, true, 4><<<L.n_launch, 256, 0, st>>>(a);
         else spmm_rows_warp_kernel<T, Ti, false, 4><<<L.n_launch, 256, 0, st>>>(a);
     } else if (L.kn == 1) {
