@@ -520,7 +520,8 @@ def test_cg_fused_dot_matches_unfused(Ti, monkeypatch):
     sol_u, hist_u = la.cg(A, bv, 30)
     monkeypatch.delenv("HPCLA_CG_UNFUSED")
     xo, ho = orc.cg(orc.distribute(G, 1, itype="i32" if Ti == np.int32 else "i64"), bvec, 30)
-    assert np.allclose(hist_f, hist_u, rtol=1e-9) and np.allclose(hist_f, ho, rtol=1e-8)
+    # the two dots round differently and CG amplifies it: agreement to 1e-7 over 30 iterations, not to the last bits
+    assert np.allclose(hist_f, hist_u, rtol=1e-7, atol=1e-12 * ho[0]) and np.allclose(hist_f, ho, rtol=1e-7, atol=1e-12 * ho[0])
     assert relerr(sol_f.to_global(), xo) <= 1e-9 and relerr(sol_u.to_global(), xo) <= 1e-9
     # a matrix with general tiles: SPD by construction, the separate dot kernel runs
     rng = np.random.default_rng(3)
