@@ -532,4 +532,4 @@ def test_cg_fused_dot_matches_unfused(Ti, monkeypatch):
     bs = rng.uniform(-1, 1, 600)
     sol, hist = la.cg(As, la.HPCVector.from_global(bs, b), 20)
     xo, ho = orc.cg(orc.distribute(S, 1, itype="i32" if Ti == np.int32 else "i64"), bs, 20)
-    assert relerr(sol.to_global(), xo) <= 1e-6 and np.allclose(hist, ho, rtol=1e-5, atol=1e-10 * ho[0])  # the tail is rounding noise
+    assert relerr(sol.to_global(), xo) <= 1e-6 and np.allclose(hist, ho, rtol=1e-5, atol=1e-8 * ho[0])  # below that the history is rounding noise (the oracle itself is not monotone there)
