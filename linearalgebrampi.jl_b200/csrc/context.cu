@@ -394,6 +394,8 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     if (const char* e = getenv("HPCLA_LANES")) lanes_override = atoi(e);
     if (const char* e = getenv("HPCLA_TILE_WINDOW")) window_override = atoi(e);
     if (const char* e = getenv("HPCLA_SPMV_KIND")) kind = (e[0] == 'g') ? 2 : (e[0] == 'r') ? 1 : 0;
+    int balance_pct = 50;  // a tile goes to the row walk when its mean row length is at least this share of its longest row
+    if (const char* e = getenv("HPCLA_BALANCE_PCT")) balance_pct = std::max(0, std::min(100, atoi(e)));
     // typical row length: the most common one (a window of whole typical rows keeps tiles row-aligned), else the mean
     double avg_row = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
     if (nrows > 0 && nnz > 0) {
@@ -423,7 +425,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         CU_TRY(launch_build_tiles(itype, d_rowptr, nrows, nnz, A->shape.window, A->d_tiles, A->ntiles, st));
         unsigned char* d_cls = nullptr;
         CU_TRY(cudaMalloc(&d_cls, (size_t)A->ntiles));
-        CU_TRY(launch_tile_class(itype, d_rowptr, A->d_tiles, A->ntiles, A->shape.window, A->shape.cap, A->shape.rp_cap, d_cls, st));
+        CU_TRY(launch_tile_class(itype, d_rowptr, A->d_tiles, A->ntiles, A->shape.window, A->shape.cap, A->shape.rp_cap, balance_pct, d_cls, st));
         A->tile_class.assign((size_t)A->ntiles, 0);
         A->h_tiles.resize((size_t)A->ntiles + 1);
         CU_TRY(cudaMemcpyAsync(A->tile_class.data(), d_cls, (size_t)A->ntiles, cudaMemcpyDeviceToHost, st));

@@ -66,8 +66,8 @@ struct SpmvLaunch {
 cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz, int window, TileDesc* tiles, i64 ntiles,
                                cudaStream_t st);
 // cls[t] = 0 (no rows), 1 (row-walk kernel), 2 (general kernel)
-cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int window, int cap, int rp_cap, unsigned char* cls,
-                              cudaStream_t st);
+cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int window, int cap, int rp_cap, int balance_pct,
+                              unsigned char* cls, cudaStream_t st);
 // hist[min(len, 1023)] += 1 for every row (hist: 1024 device counters, pre-zeroed)
 cudaError_t launch_row_len_hist(int itype, const void* rowptr, i64 nrows, unsigned long long* hist, cudaStream_t st);
 // rows longer than threshold: writes their local row ids (ascending not guaranteed) into rows_out (capacity cap), count via *count_out (device)

@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(256) classify_tiles_kernel(const Ti* __restric
 // lanes of the walk are well used), 2 = general kernel.
 template <class Ti>
 __global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ rowptr, const TileDesc* __restrict__ tiles, i64 ntiles, int window, int cap,
-                                                         int rp_cap, unsigned char* cls) {
+                                                         int rp_cap, int balance_pct, unsigned char* cls) {
     const i64 t = (i64)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (t >= ntiles) return;
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) tile_class_kernel(const Ti* __restrict__ 
     }
     // staged from the window start; rp_cap - 8 rows is also what a tile header of the direct walk holds
     const bool fits = (e - t * (i64)window) <= (i64)cap && (r1 + 1 - (r0 & ~(i64)3)) <= (i64)rp_cap && (r1 - r0) <= (i64)(rp_cap - 8);
-    const bool balanced = 2 * (e - s) >= (r1 - r0) * maxlen;
+    const bool balanced = 100 * (e - s) >= (i64)balance_pct * (r1 - r0) * maxlen;  // mean row length >= balance_pct % of the longest
     if (lane == 0) cls[t] = (fits && balanced && e > s) ? 1 : 2;
 }
 
@@ -646,6 +646,8 @@ static TileShape shape_of(int itype, double avg_row, bool irregular, int lanes_o
         s.ovf = (((int)avg_row + 4) + 3) & ~3;
         if (s.ovf > slack) s.ovf = slack;
         s.hdr_rows = 2 * (ROW_THREADS / G);  // boundary rows of a stencil are shorter: up to twice the typical row count
+        const int by_window = (int)(2.0 * s.window / (avg_row > 1.0 ? avg_row : 1.0));  // (a window override may hold more rows)
+        if (by_window > s.hdr_rows) s.hdr_rows = (by_window + 7) & ~7;
         if (s.cap > 65535) s.hdr_rows = 0;  // offsets would not fit 16 bits: no direct walk
         s.hdr_bytes = (16 + 2 * (s.hdr_rows + 1) + 15) & ~15;
         s.rp_cap = (s.hdr_rows + 8 + 3) & ~3;
@@ -670,12 +672,12 @@ cudaError_t launch_build_tiles(int itype, const void* rowptr, i64 nrows, i64 nnz
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int window, int cap, int rp_cap, unsigned char* cls,
-                              cudaStream_t st) {
+cudaError_t launch_tile_class(int itype, const void* rowptr, const TileDesc* tiles, i64 ntiles, int window, int cap, int rp_cap, int balance_pct,
+                              unsigned char* cls, cudaStream_t st) {
     if (ntiles == 0) return cudaSuccess;
     const int blocks = blocks_for(ntiles, 8);
-    if (itype == HPCLA_I32) tile_class_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, tiles, ntiles, window, cap, rp_cap, cls);
-    else tile_class_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, tiles, ntiles, window, cap, rp_cap, cls);
+    if (itype == HPCLA_I32) tile_class_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, tiles, ntiles, window, cap, rp_cap, balance_pct, cls);
+    else tile_class_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, tiles, ntiles, window, cap, rp_cap, balance_pct, cls);
     return cudaGetLastError();
 }
 
