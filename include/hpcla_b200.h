@@ -40,6 +40,7 @@ typedef struct hpcla_plan hpcla_plan;   /* index fields of a VectorPlan (src/vec
 typedef struct hpcla_spmv hpcla_spmv;   /* (csr, plan) bound to device buffers: what `A*x` / `mul!` execute         */
 typedef struct hpcla_tb hpcla_tb;       /* TransposePlan under construction / its result (src/sparse.jl:1519-1538) */
 typedef struct hpcla_dtb hpcla_dtb;     /* the same result, built and held on the device                          */
+typedef struct hpcla_spgemm hpcla_spgemm; /* memoised symbolic product of A and the gathered rows of B              */
 
 int hpcla_abi_version(void);
 const char* hpcla_last_error(void);
@@ -190,6 +191,32 @@ int hpcla_spmv_info(const hpcla_spmv* op, int64_t* n_interior_tiles, int64_t* n_
 /* kernel launches enqueued by this operator so far (bench.py's gpu_launches) */
 int64_t hpcla_spmv_launch_count(const hpcla_spmv* op);
 void hpcla_spmv_destroy(hpcla_spmv* op);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sparse x sparse, A * B::HPCSparseMatrix — replaces the body of Base.:*(A, B), src/sparse.jl:991-1059,
+ * which copies both operands to the host and calls SparseArrays' `plan.AT * A_csc` (symbolic + numeric) on every call.
+ *   symbolic  (once per pair of structures, host): A's local CSR (rowptr, colval = 1-based position in A.col_indices,
+ *             i.e. the number of the gathered row of B) and the structure of the gathered rows B[A.col_indices, :]
+ *             (bg_rowptr: Int64[n+1], 1-based; bg_cols: GLOBAL 1-based columns, ascending within a row — what the
+ *             reference's MatrixPlan receives, src/sparse.jl:579-897) -> structure of the local block of C and, per
+ *             stored entry of C, the (entry of A, entry of gathered B) pairs that feed it, ascending in the shared index.
+ *   sizes     stored entries of C, compressed columns, product terms
+ *   structure rowptr Ti[nrows+1], colval Ti[nnz] (compressed), col_indices Int64[ncc] (src/sparse.jl:1018-1040)
+ *   numeric   (every call, device): C.nzval[d] = sum of Bg.nzval[ib] * A.nzval[ia] over the pairs of d, in order: the
+ *             values of the reference, bit for bit; cancelled entries are kept as stored zeros, as there.
+ *             d_bg_nzval: the values of the gathered rows in the order of bg_cols (execute_plan!, src/sparse.jl:922-983). */
+int hpcla_spgemm_symbolic(int itype, int64_t nrows_local, const void* a_rowptr, const void* a_colval,
+                          int64_t n_gathered_rows, const int64_t* bg_rowptr, const int64_t* bg_cols, hpcla_spgemm** out);
+int hpcla_spgemm_sizes(const hpcla_spgemm* plan, int64_t* nnz_out, int64_t* ncc_out, int64_t* nterms_out);
+int hpcla_spgemm_structure(const hpcla_spgemm* plan, int itype, void* rowptr_out, void* colval_out, int64_t* col_indices_out);
+int hpcla_spgemm_numeric(hpcla_spgemm* plan, hpcla_ctx* ctx, int dtype, const void* d_a_nzval, const void* d_bg_nzval,
+                         void* d_c_nzval, void* stream);
+void hpcla_spgemm_destroy(hpcla_spgemm* plan);
+/* All-to-all of byte ranges between device buffers: rank q gets d_send[send_off[q] .. +send_bytes[q]) into its
+ * d_recv[recv_off[me] ..); grouped ncclSend/ncclRecv, the own range is a device-to-device copy.  The value exchange of
+ * a MatrixPlan (tag 3 of src/sparse.jl:945-975) without host staging.  Collective (NCCL world or nranks == 1). */
+int hpcla_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const int64_t* send_off, const int64_t* send_bytes,
+                         void* d_recv, const int64_t* recv_off, const int64_t* recv_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * HPCVector reductions and updates used by iterative solvers.

@@ -21,7 +21,11 @@ from .sparse import (  # noqa: F401
     vec_adjoint_mul, vec_transpose_mul,
 )
 from .dense import HPCMatrix, spmm  # noqa: F401
+from .spgemm import MatrixPlan, get_matrix_plan, spgemm  # noqa: F401
 from . import sparse, synth, vectors, backends, dense  # noqa: F401
+import importlib as _importlib
+
+spgemm_module = _importlib.import_module(__name__ + ".spgemm")  # the submodule (the name `spgemm` is the function)
 
 HPCVector_local = HPCVector.from_local
 HPCMatrix_local = HPCMatrix.from_local

@@ -91,6 +91,12 @@ SIGNATURES = {
     "hpcla_spmv_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "hpcla_spmv_launch_count": (_i64, [_vp]),
     "hpcla_spmv_destroy": (None, [_vp]),
+    "hpcla_spgemm_symbolic": (_i, [_i, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "hpcla_spgemm_sizes": (_i, [_vp, _vp, _vp, _vp]),
+    "hpcla_spgemm_structure": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "hpcla_spgemm_numeric": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "hpcla_spgemm_destroy": (None, [_vp]),
+    "hpcla_exchange_bytes": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_dot": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp]),
     "hpcla_nrm2": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "hpcla_axpby": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -152,6 +152,10 @@ class HPCSparseMatrix:
 
         if isinstance(x, HPCMatrix):  # Base.:*(A::HPCSparseMatrix, B::HPCMatrix) — src/sparse.jl:2391-2413
             return spmm(self, x)
+        if isinstance(x, HPCSparseMatrix):  # Base.:*(A::HPCSparseMatrix, B::HPCSparseMatrix) — src/sparse.jl:991-1059
+            from .spgemm import spgemm
+
+            return spgemm(self, x)
         return NotImplemented
 
     @property
@@ -313,15 +317,20 @@ def clear_plan_cache() -> None:
     """clear_plan_cache!() — src/HPCLinearAlgebra.jl:181-201."""
     from . import vectors as _v
 
+    from .spgemm import _matrix_plan_cache  # (the package attribute `spgemm` is the function, not the module)
+
     _vector_plan_cache.clear()
     _v._repartition_plan_cache.clear()
+    _matrix_plan_cache.clear()
 
 
 def cache_sizes() -> Dict[str, int]:
     """cache_sizes() — src/HPCLinearAlgebra.jl:208-244 (only the cache this path owns)."""
     from . import vectors as _v
 
-    return {"vector_plan": len(_vector_plan_cache), "repartition_plan": len(_v._repartition_plan_cache)}
+    from .spgemm import _matrix_plan_cache
+
+    return {"vector_plan": len(_vector_plan_cache), "repartition_plan": len(_v._repartition_plan_cache), "matrix_plan": len(_matrix_plan_cache)}
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -350,6 +350,73 @@ def repartition(xs: Sequence[np.ndarray], old_partition, new_partition) -> List[
     return out
 
 
+def gather_rows(locsB: Sequence[LocalMatrix], row_indices: np.ndarray):
+    """What MatrixPlan(row_indices, B) + execute_plan! leave in plan.AT (src/sparse.jl:579-983): the rows
+    B[row_indices, :] (sorted global 1-based row ids) as (rowptr 1-based int64, GLOBAL 1-based columns, values), each
+    row fetched from its owner in B.row_partition."""
+    rpB = np.asarray(locsB[0].row_partition, dtype=np.int64)
+    rowptr, cols, vals = [1], [], []
+    for g in np.asarray(row_indices, dtype=np.int64):
+        o = int(np.searchsorted(rpB, g, side="right")) - 1
+        o = min(max(o, 0), len(locsB) - 1)
+        m = locsB[o]
+        i = int(g - rpB[o])
+        b, e = int(m.rowptr[i]) - 1, int(m.rowptr[i + 1]) - 1
+        cols.append(np.asarray(m.col_indices, dtype=np.int64)[np.asarray(m.colval[b:e], dtype=np.int64) - 1])
+        vals.append(np.asarray(m.nzval[b:e]))
+        rowptr.append(rowptr[-1] + (e - b))
+    dt = locsB[0].nzval.dtype
+    return (np.asarray(rowptr, dtype=np.int64), np.concatenate(cols) if cols else np.zeros(0, np.int64),
+            np.concatenate(vals) if vals else np.zeros(0, dt))
+
+
+def spgemm(locsA: Sequence[LocalMatrix], locsB: Sequence[LocalMatrix], itype="i64") -> List[LocalMatrix]:
+    """Base.:*(A::HPCSparseMatrix, B::HPCSparseMatrix) on all ranks (src/sparse.jl:991-1059): gather B[A.col_indices, :],
+    then CT = plan.AT * A_csc — SparseArrays' spmatmul: for every local row i of A (a column of A_csc), for its stored
+    entries k ascending, for the stored entries (c, b) of gathered row k: CT[c, i] += b * a.  Output columns ascending,
+    entries that cancel are kept.  Result block: row_partition = A.row_partition, col_partition = B.col_partition,
+    col_indices = unique(sort(columns)), compressed colval (:1018-1040)."""
+    out = []
+    for A in locsA:
+        bg_rowptr, bg_cols, bg_vals = gather_rows(locsB, A.col_indices)
+        rowptr, gcols, vals = [1], [], []
+        for i in range(A.nrows_local):
+            acc, order = {}, []
+            for j in range(int(A.rowptr[i]) - 1, int(A.rowptr[i + 1]) - 1):
+                g = int(A.colval[j]) - 1
+                a = A.nzval[j]
+                for q in range(int(bg_rowptr[g]) - 1, int(bg_rowptr[g + 1]) - 1):
+                    c = int(bg_cols[q])
+                    if c in acc:
+                        acc[c] = acc[c] + bg_vals[q] * a
+                    else:
+                        acc[c] = bg_vals[q] * a
+                        order.append(c)
+            for c in sorted(order):
+                gcols.append(c)
+                vals.append(acc[c])
+            rowptr.append(rowptr[-1] + len(order))
+        dt = A.nzval.dtype
+        out.append(local_matrix(A.rank, np.asarray(rowptr, dtype=np.int64), np.asarray(gcols, dtype=np.int64), np.asarray(vals, dtype=dt), A.row_partition,
+                                locsB[0].col_partition, itype))
+    return out
+
+
+def to_global(locals_: Sequence[LocalMatrix], shape):
+    """The distributed matrix back as one scipy CSR (explicit zeros kept)."""
+    import scipy.sparse as sp
+
+    rows, cols, vals = [], [], []
+    for m in locals_:
+        r0 = int(m.row_partition[m.rank]) - 1
+        for i in range(m.nrows_local):
+            b, e = int(m.rowptr[i]) - 1, int(m.rowptr[i + 1]) - 1
+            rows += [r0 + i] * (e - b)
+            cols += (np.asarray(m.col_indices, dtype=np.int64)[np.asarray(m.colval[b:e], dtype=np.int64) - 1] - 1).tolist()
+            vals += list(m.nzval[b:e])
+    return sp.csr_matrix((np.asarray(vals), (np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64))), shape=shape)
+
+
 def matmat(locals_: Sequence[LocalMatrix], B_global: np.ndarray, b_row_partition=None) -> np.ndarray:
     """A * B for a dense B, the reference's way (src/sparse.jl:2391-2413): for every column k, `A * B[:, k]` with the
     column's partition = B's row partition (src/indexing.jl:385-393), results concatenated column by column."""

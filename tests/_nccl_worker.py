@@ -103,6 +103,14 @@ def main():
         assert np.array_equal(yv.local_values(), orc.repartition(orc.split_vector(vh, old), old, new)[rank])
         zv = la.HPCVector.from_global(vh, b, partition=new)
         assert abs(la.dot(xv, zv) - np.vdot(vh, vh)) <= 1e-9 * n
+    # 2c. sparse x sparse over NCCL: structure gathered on the host communicator, values exchanged between devices
+    b = la.backend_cuda_mpi(np.float64, np.int32, comm=comm, device=local_rank)
+    Ag = sp.random(400, 300, density=0.03, random_state=np.random.default_rng(12), format="csr")
+    Bg2 = sp.random(300, 350, density=0.04, random_state=np.random.default_rng(13), format="csr")
+    Cm = la.HPCSparseMatrix.from_global(Ag, b) * la.HPCSparseMatrix.from_global(Bg2, b)
+    oC = orc.spgemm(orc.distribute(Ag, P, itype="i32"), orc.distribute(Bg2, P, itype="i32"), itype="i32")[rank]
+    assert np.array_equal(Cm.rowptr, oC.rowptr) and np.array_equal(Cm.colval, oC.colval) and np.array_equal(Cm.col_indices, oC.col_indices)
+    assert np.array_equal(Cm.nzval_host(), oC.nzval), "A*B values"
     # 3. reductions + CG over NCCL
     b = la.backend_cuda_mpi(np.float64, np.int32, comm=comm, device=local_rank)
     N = 20

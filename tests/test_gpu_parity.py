@@ -533,3 +533,46 @@ def test_cg_fused_dot_matches_unfused(Ti, monkeypatch):
     sol, hist = la.cg(As, la.HPCVector.from_global(bs, b), 20)
     xo, ho = orc.cg(orc.distribute(S, 1, itype="i32" if Ti == np.int32 else "i64"), bs, 20)
     assert relerr(sol.to_global(), xo) <= 1e-6 and np.allclose(hist, ho, rtol=1e-5, atol=1e-8 * ho[0])  # below that the history is rounding noise (the oracle itself is not monotone there)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sparse x sparse: memoised symbolic product + numeric kernel vs the restatement of Base.:*(A, B)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T,Ti", [(np.float64, np.int32), (np.complex128, np.int64), (np.float32, np.int32)])
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_sparse_times_sparse(T, Ti, P):
+    rng = np.random.default_rng(300 + P)
+    S = la.synth
+    rp, c, v = S.stencil_local(1, 10, 0, 1000, T, Ti)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(1000, 1000))
+    cases = [(G, G), (_ragged(rng, 300, 200, 0.03, T), _ragged(rng, 200, 260, 0.05, T))]
+    itype = "i32" if Ti == np.int32 else "i64"
+    for A, B in cases:
+        A, B = sp.csr_matrix(A).astype(T), sp.csr_matrix(B).astype(T)
+
+        def body(rank, bs):
+            b = bs[rank]
+            torch.cuda.set_device(b.torch_device())
+            Am, Bm = la.HPCSparseMatrix.from_global(A, b), la.HPCSparseMatrix.from_global(B, b)
+            C = Am * Bm
+            assert isinstance(C, la.HPCSparseMatrix) and C.row_partition.tolist() == Am.row_partition.tolist() and C.col_partition.tolist() == Bm.col_partition.tolist()
+            n0 = len(la.spgemm_module._matrix_plan_cache)
+            # new values, same structure: the numeric phase alone (in-place writes are seen, the plan is reused)
+            Bm.nzval.mul_(2.0)
+            C2 = Am * Bm
+            assert len(la.spgemm_module._matrix_plan_cache) == n0
+            x = S.vector(B.shape[1], b)
+            y = C * x  # the product is a first-class operand of the hot path
+            return (C.rowptr, C.colval, C.col_indices, C.nzval_host()), C2.nzval_host(), y.to_global()
+
+        la.clear_plan_cache()
+        res = spmd(backends(P, T, Ti), body)
+        lC = orc.spgemm(orc.distribute(A, P, itype=itype), orc.distribute(B, P, itype=itype), itype=itype)
+        xh = S.vector_local(T, S.X_SEED, 0, B.shape[1])
+        y_ref = (A @ (B @ xh))
+        for r, ((rowptr, colval, ci, vals), vals2, y) in enumerate(res):
+            o = lC[r]
+            assert np.array_equal(rowptr, o.rowptr) and np.array_equal(colval, o.colval) and np.array_equal(ci, o.col_indices)
+            assert np.array_equal(vals, o.nzval), "same terms, same order, products rounded separately: the reference's values bit for bit"
+            assert np.array_equal(vals2, 2 * o.nzval)
+            assert relerr(y, y_ref) <= (1e-4 if T == np.float32 else 1e-12)

@@ -375,3 +375,46 @@ def test_repartition_plan_matches_the_restatement(P):
         assert [len(o) for o in out] == np.diff(new).tolist()
     with pytest.raises(la.HPCLAError):
         la.VectorRepartitionPlan(0, P, orc.uniform_partition(5, P), orc.uniform_partition(6, P))
+
+
+@pytest.mark.parametrize("P", [1, 2, 4])
+def test_matrix_plan_and_symbolic_product_match_the_restatement(P):
+    """MatrixPlan(A, B) (structure of B[A.col_indices, :], src/sparse.jl:579-897) and the memoised symbolic product
+    (hpcla_spgemm_symbolic) against the oracle's restatement of Base.:*(A, B) (src/sparse.jl:991-1059): gathered
+    pattern, rowptr, compressed colval and col_indices of every rank's block, bit for bit; rectangular operands, empty
+    rows, non-uniform partitions.  No device needed: the symbolic phase is host code."""
+    rng = np.random.default_rng(20 + P)
+    cases = []
+    for (m, k, n, da, db) in [(60, 45, 70, 0.15, 0.1), (33, 80, 20, 0.05, 0.3), (10, 10, 10, 0.0, 0.5)]:
+        A = sp.random(m, k, density=da, random_state=rng, format="lil")
+        B = sp.random(k, n, density=db, random_state=rng, format="lil")
+        if m > 3:
+            A[1, :] = 0  # an empty row
+        cases.append((sp.csr_matrix(A), sp.csr_matrix(B)))
+    for A, B in cases:
+        m, k = A.shape
+        rpA = np.concatenate([[1], np.sort(rng.integers(1, m + 2, size=P - 1)), [m + 1]]).astype(np.int64)
+        rpB = np.concatenate([[1], np.sort(rng.integers(1, k + 2, size=P - 1)), [k + 1]]).astype(np.int64)
+        lA = orc.distribute(A, P, row_partition=rpA, itype="i32")
+        lB = orc.distribute(B, P, row_partition=rpB, itype="i32")
+        lC = orc.spgemm(lA, lB, itype="i32")
+        ref = sp.csr_matrix(A @ B)
+        assert abs(orc.to_global(lC, ref.shape) - ref).max() <= 1e-13
+        bs = la.backends_threads(P, np.float64, np.int32, cuda=False)
+
+        def body(rank, bs):
+            b = bs[rank]
+            Am = la.HPCSparseMatrix.from_global(A, b, row_partition=rpA)
+            Bm = la.HPCSparseMatrix.from_global(B, b, row_partition=rpB)
+            plan = la.get_matrix_plan(Am, Bm)
+            assert la.get_matrix_plan(Am, Bm) is plan  # memoised (src/sparse.jl:900-916)
+            bg = orc.gather_rows(lB, lA[rank].col_indices)
+            o = lC[rank]
+            assert np.array_equal(plan.bg_rowptr, bg[0]) and np.array_equal(plan.bg_cols, bg[1])
+            assert np.array_equal(plan.rowptr, o.rowptr) and np.array_equal(plan.colval, o.colval) and np.array_equal(plan.col_indices, o.col_indices)
+            with pytest.raises(la.HPCLAError):
+                Am * Bm  # structure-only backend: no CPU arithmetic
+            return True
+
+        la.clear_plan_cache()
+        assert all(bs[0].comm.world.run(body, bs))
