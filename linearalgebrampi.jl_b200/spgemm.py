@@ -98,7 +98,8 @@ class MatrixPlan:
         self.colval = np.empty(self.nnz, dtype=b.Ti)
         self.col_indices = np.empty(self.ncc, dtype=np.int64)
         _lib.check(L.hpcla_spgemm_structure(self.handle, _lib.itype_code(b.Ti), _lib.ptr(self.rowptr), _lib.ptr(self.colval), _lib.ptr(self.col_indices)))
-        self._dev = None  # device copies of send positions / structure, made on first execution
+        self._dev = None  # device copy of the send positions, made on first execution
+        self._structure_dev = None  # device copies of C's rowptr / colval, shared by every product of this plan
 
     def __del__(self):
         try:
@@ -185,7 +186,10 @@ def spgemm(A: HPCSparseMatrix, B: HPCSparseMatrix) -> HPCSparseMatrix:
     _lib.check(_lib.lib().hpcla_spgemm_numeric(plan.handle, b.ctx().handle, _lib.dtype_code(b.T), _lib.ptr(A.nzval), _lib.ptr(bg_vals), _lib.ptr(nzval),
                                                _current_stream(b)))
     nzval._hpcla_keepalive = bg_vals
-    rowptr_t = torch.from_numpy(plan.rowptr).to(dev)
-    colval_t = torch.from_numpy(plan.colval).to(dev)
-    return HPCSparseMatrix(None, A.row_partition.copy(), B.col_partition.copy(), plan.col_indices.copy(), plan.rowptr.copy(), plan.colval.copy(), nzval,
+    # the structure of C is part of the memoised plan: every product shares the same (read-only) structure arrays, on the
+    # host and on the device; only nzval is new
+    if plan._structure_dev is None:
+        plan._structure_dev = (torch.from_numpy(plan.rowptr).to(dev), torch.from_numpy(plan.colval).to(dev))
+    rowptr_t, colval_t = plan._structure_dev
+    return HPCSparseMatrix(None, A.row_partition.copy(), B.col_partition.copy(), plan.col_indices, plan.rowptr, plan.colval, nzval,
                            A.nrows_local, plan.ncc, rowptr_t, colval_t, b)

@@ -6,6 +6,7 @@
   f.1 sparse x dense: hpcla_spmm_run against the reference's column loop (ncols SpMVs), Poisson 256^3 per GPU
   f.2 repartition:    uniform -> shifted partition of a 256^3-per-GPU Float64 vector (bytes that change owner / time)
   f.3 transpose:      hpcla_transpose_device against the host builder, 27-point 128^3 ComplexF64
+  f.4 sparse x sparse: A*A for the 7-point Poisson matrix, 96^3 rows per GPU: first call (plan + symbolic) and numeric phase
 """
 import json
 import os
@@ -98,6 +99,29 @@ def main():
     os.environ.pop("HPCLA_TRANSPOSE", None)
     emit(row="f.3 transpose materialisation", grid=(N, N, N), nnz_local=Ac.nnz_local, device_s=out["device"], host_s=out["host"], speedup=out["host"] / out["device"],
          note="wall clock including the read-back of rowptr/colval that the Python mirror keeps on the host")
+    # ---- f.4 -----------------------------------------------------------------------------------------------------
+    Ns = 96
+    As = S.stencil_matrix(1, (Ns, Ns, Ns * world), b)
+    la.clear_plan_cache()
+    sync()
+    t0 = time.time()
+    C = As * As  # MatrixPlan + symbolic product (host, memoised) + first numeric pass
+    sync()
+    t_first = time.time() - t0
+    plan = la.get_matrix_plan(As, As)
+    t_num = timed(lambda: la.spgemm(As, As), 10, sync)
+    cpu_s = None
+    if world == 1:
+        import scipy.sparse as sp
+
+        rp, c, v = S.stencil_local(1, (Ns, Ns, Ns), 0, Ns**3, np.float64, np.int32)
+        G = sp.csr_matrix((v, c - 1, rp - 1), shape=(Ns**3, Ns**3))
+        t0 = time.time()
+        G @ G
+        cpu_s = time.time() - t0
+    emit(row="f.4 sparse x sparse (A*A, 7-point Poisson)", grid=(Ns, Ns, Ns * world), nnz_c_local=plan.nnz, terms_local=plan.nterms, first_call_s=t_first,
+         numeric_ms=t_num, host_scipy_csr_matmul_s=cpu_s,
+         note="first call = structure gather + symbolic product on the host (memoised); later calls = value exchange + one kernel; scipy = one-core host product, for scale")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
