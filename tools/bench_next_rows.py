@@ -87,17 +87,17 @@ def main():
     N = 128
     Ac = S.stencil_matrix(2, N, bc)
     out = {}
-    for mode in ("device", "host"):
+    for mode in ("device", "host", "device"):  # the first device build also pays NCCL's lazy connection set-up
         os.environ["HPCLA_TRANSPOSE"] = mode
         Ac.cached_transpose = None
         sync()
         t0 = time.time()
         Y = la.materialize_transpose(Ac)
         sync()
-        out[mode] = time.time() - t0
+        out[mode if mode not in out else mode + "_again"] = time.time() - t0
         del Y
     os.environ.pop("HPCLA_TRANSPOSE", None)
-    emit(row="f.3 transpose materialisation", grid=(N, N, N), nnz_local=Ac.nnz_local, device_s=out["device"], host_s=out["host"], speedup=out["host"] / out["device"],
+    emit(row="f.3 transpose materialisation", grid=(N, N, N), nnz_local=Ac.nnz_local, device_first_s=out["device"], device_s=out["device_again"], host_s=out["host"], speedup=out["host"] / out["device_again"],
          note="wall clock including the read-back of rowptr/colval that the Python mirror keeps on the host")
     # ---- f.4 -----------------------------------------------------------------------------------------------------
     Ns = 96
