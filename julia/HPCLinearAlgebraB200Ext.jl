@@ -165,6 +165,37 @@ function Base.:*(A::HPCSparseMatrix{T,Ti,B}, Bm::HPCMatrix{T,B}) where {T,Ti,B<:
     return HPCMatrix_local(C, A.backend)
 end
 
+# --- A * B::HPCSparseMatrix: replaces the host product of src/sparse.jl:991-1059.  The reference's MatrixPlan (structure of
+#     B[A.col_indices, :], memoised, src/sparse.jl:579-916) stays as it is; the symbolic product is memoised next to it and
+#     every later product is: values of the gathered rows (execute_plan! into a device target, :922-983), one kernel.
+const _spgemm = Dict{Any,Ptr{Cvoid}}()
+function Base.:*(A::HPCSparseMatrix{T,Ti,B}, Bm::HPCSparseMatrix{T,Ti,B}) where {T,Ti,B<:CuB}
+    plan = MatrixPlan(A, Bm)                                          # memoised by the reference
+    key = (_ensure_hash(A), _ensure_hash(Bm), T, Ti)
+    h = get!(_spgemm, key) do
+        AT = plan.AT                                                  # CSC of B[A.col_indices, :]^T: colptr = row pointers, rowval = GLOBAL columns
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        _check(@ccall(libhpcla.hpcla_spgemm_symbolic(_itype(Ti)::Cint, Int64(A.nrows_local)::Int64, A.rowptr::Ptr{Cvoid}, A.colval::Ptr{Cvoid},
+                  Int64(length(A.col_indices))::Int64, Int64.(AT.colptr)::Ptr{Int64}, Int64.(AT.rowval)::Ptr{Int64}, out::Ptr{Ptr{Cvoid}})::Cint),
+               "hpcla_spgemm_symbolic")
+        out[]
+    end
+    nnz = Ref{Int64}(0); ncc = Ref{Int64}(0); nt = Ref{Int64}(0)
+    _check(@ccall(libhpcla.hpcla_spgemm_sizes(h::Ptr{Cvoid}, nnz::Ptr{Int64}, ncc::Ptr{Int64}, nt::Ptr{Int64})::Cint), "hpcla_spgemm_sizes")
+    rowptr = zeros(Ti, A.nrows_local + 1); colval = zeros(Ti, nnz[]); col_indices = zeros(Int, ncc[])
+    _check(@ccall(libhpcla.hpcla_spgemm_structure(h::Ptr{Cvoid}, _itype(Ti)::Cint, rowptr::Ptr{Cvoid}, colval::Ptr{Cvoid}, col_indices::Ptr{Int64})::Cint),
+           "hpcla_spgemm_structure")
+    bg = CUDA.zeros(T, length(plan.AT.nzval))
+    execute_plan!(plan, Bm, bg)                                       # the reference's value gather with a device target (src/sparse.jl:922-983)
+    nzval = CUDA.zeros(T, nnz[])
+    GC.@preserve A bg nzval begin
+        _check(@ccall(libhpcla.hpcla_spgemm_numeric(h::Ptr{Cvoid}, _context(A.backend)::Ptr{Cvoid}, _dtype(T)::Cint, _dptr(A.nzval)::Ptr{Cvoid},
+                  _dptr(bg)::Ptr{Cvoid}, _dptr(nzval)::Ptr{Cvoid}, _stream()::Ptr{Cvoid})::Cint), "hpcla_spgemm_numeric")
+    end
+    return HPCSparseMatrix{T,Ti,B}(nothing, A.row_partition, Bm.col_partition, col_indices, rowptr, colval, nzval, A.nrows_local, ncc[], nothing, nothing,
+                                   CuVector(rowptr), CuVector(colval), A.backend)              # as src/sparse.jl:1054-1058
+end
+
 # --- repartition(x, p): replaces VectorRepartitionPlan + execute_plan! (src/vectors.jl:519-676: host-staged, tag 92) ------------
 function HPCLinearAlgebra.repartition(x::HPCVector{T,B}, p::Vector{Int}) where {T,B<:CuB}
     (x.partition === p || x.partition == p) && return x              # the reference's fast path (src/vectors.jl:714-716)
