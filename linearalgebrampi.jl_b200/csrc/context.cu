@@ -183,8 +183,6 @@ struct hpcla_spmv {
     void* mm_C = nullptr;
     i64 mm_ldb = 0, mm_ldc = 0;
     int mm_ncols = 0;
-    const void* persist_x = nullptr;  // x.v currently covered by the L2 persisting window (HPCLA_X_PERSIST)
-    cudaStream_t persist_stream = nullptr;
     std::atomic<long long> epoch{0};  // exchanges begun (a peer's finish checks that I have begun the matching one)
     i64 launches = 0;
 };
@@ -869,40 +867,6 @@ static int launch_long(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stre
     return HPCLA_OK;
 }
 
-// Experiment hook, HPCLA_X_PERSIST=<percent>: mark x.v as an L2 persisting access window on the caller's stream (hit
-// ratio = percent / 100), so that scattered gathers of an x larger than the effective L2 keep a resident fraction.
-static void maybe_persist_x(hpcla_spmv* op, const void* d_x, cudaStream_t stream) {
-    static int pct = -1;
-    if (pct < 0) {
-        const char* e = getenv("HPCLA_X_PERSIST");
-        pct = e ? atoi(e) : 0;
-    }
-    if (pct <= 0 || !d_x || (op->persist_x == d_x && op->persist_stream == stream)) return;
-    int max_persist = 0, max_window = 0;
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, op->ctx->device);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, op->ctx->device);
-    if (max_persist <= 0 || max_window <= 0) return;
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
-    cudaStreamAttrValue v;
-    std::memset(&v, 0, sizeof v);
-    const size_t bytes = (size_t)op->n_x_local * dtype_size(op->csr->dtype);
-    v.accessPolicyWindow.base_ptr = const_cast<void*>(d_x);
-    v.accessPolicyWindow.num_bytes = bytes < (size_t)max_window ? bytes : (size_t)max_window;
-    v.accessPolicyWindow.hitRatio = pct >= 100 ? 1.0f : (float)pct / 100.0f;
-    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    cudaError_t e = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
-    static bool told = false;
-    if (!told) {
-        fprintf(stderr, "[hpcla] HPCLA_X_PERSIST=%d: max persisting L2 %d MiB, max window %d MiB, x %zu MiB: %s\n", pct, max_persist >> 20, max_window >> 20,
-                bytes >> 20, cudaGetErrorString(e));
-        told = true;
-    }
-    cudaGetLastError();
-    op->persist_x = d_x;
-    op->persist_stream = stream;
-}
-
 extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream_) {
     if (!op || (op->n_x_local > 0 && !d_x) || (op->csr->nrows > 0 && !d_y)) return fail(HPCLA_ERR_ARG, "hpcla_spmv_begin: null");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_begin: the previous call was not finished");
@@ -912,7 +876,6 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     op->cur_x = d_x;
     op->cur_y = d_y;
     op->cur_stream = stream;
-    maybe_persist_x(op, d_x, stream);
     if (op->has_peers) {
         rc = exchange_begin(op, d_x, stream);
         if (rc) return rc;
@@ -1254,7 +1217,6 @@ extern "C" int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x,
     op->cur_x = d_x;
     op->cur_y = d_y;
     op->cur_stream = stream;
-    maybe_persist_x(op, d_x, stream);
     if (op->has_peers) {
         rc = exchange_begin(op, d_x, stream, P->ev_in[(size_t)nb - 1]);
         if (rc) return rc;
