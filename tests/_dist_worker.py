@@ -39,6 +39,23 @@ def main():
     rp_, c_, v_ = la.synth.stencil_local(la.synth.POISSON3D_7PT, 6, 0, 216, np.float64, np.int32)
     G = sp.csr_matrix((v_, c_ - 1, rp_ - 1), shape=(216, 216))
     _compare_matrix(A, orc.distribute(G, P, itype="i32")[rank])
+    # the next rows over the real process group: MatrixPlan structure exchange (tags 1, 2) + symbolic product, repartition
+    # plans, HPCMatrix_local's Allgather of row counts
+    Bs = sp.random(280, 150, density=0.05, random_state=np.random.default_rng(6), format="csr")
+    b = la.backend_cpu_mpi(np.float64, np.int64, comm=comm)
+    Am, Bm = la.HPCSparseMatrix.from_global(R, b), la.HPCSparseMatrix.from_global(Bs, b)
+    lA, lB = orc.distribute(R, P, itype="i64"), orc.distribute(Bs, P, itype="i64")
+    mp = la.get_matrix_plan(Am, Bm)
+    oC = orc.spgemm(lA, lB, itype="i64")[rank]
+    bg = orc.gather_rows(lB, lA[rank].col_indices)
+    assert np.array_equal(mp.bg_rowptr, bg[0]) and np.array_equal(mp.bg_cols, bg[1])
+    assert np.array_equal(mp.rowptr, oC.rowptr) and np.array_equal(mp.colval, oC.colval) and np.array_equal(mp.col_indices, oC.col_indices)
+    old, new = orc.uniform_partition(37, P), np.array([1, 30, 38], dtype=np.int64)
+    rpl, ref = la.VectorRepartitionPlan(rank, P, old, new), orc.repartition_plan(rank, old, new)
+    assert rpl.send_rank_ids == ref["send_rank_ids"] and rpl.recv_offsets == ref["recv_offsets"] and rpl.result_local_size == ref["result_local_size"]
+    M = np.arange(20.0).reshape(10, 2)
+    lo, hi = int(orc.uniform_partition(10, P)[rank]) - 1, int(orc.uniform_partition(10, P)[rank + 1]) - 1
+    assert np.array_equal(la.HPCMatrix_local(M[lo:hi], b).to_global(), M)
     assert la.comm_allreduce(comm, rank + 1) == P * (P + 1) // 2
     dist.barrier()
     print("DIST_OK", flush=True)

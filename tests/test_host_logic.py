@@ -418,3 +418,31 @@ def test_matrix_plan_and_symbolic_product_match_the_restatement(P):
 
         la.clear_plan_cache()
         assert all(bs[0].comm.world.run(body, bs))
+
+
+def test_next_row_entry_points_reject_bad_arguments():
+    """Argument errors of the host-side entry points added for SURVEY §8(f): status code + message, never an abort."""
+    L = la._lib.lib()
+    import ctypes
+
+    h = ctypes.c_void_p()
+    rowptr = np.array([1, 3], dtype=np.int32)
+    colval = np.array([1, 5], dtype=np.int32)  # gathered row 5 of 2
+    bg_rowptr = np.array([1, 2, 3], dtype=np.int64)
+    bg_cols = np.array([1, 2], dtype=np.int64)
+    rc = L.hpcla_spgemm_symbolic(la._lib.I32, 1, la._lib.ptr(rowptr), la._lib.ptr(colval), 2, la._lib.ptr(bg_rowptr), la._lib.ptr(bg_cols), ctypes.byref(h))
+    assert rc == 1 and b"gathered row 5 of 2" in L.hpcla_last_error()
+    assert L.hpcla_spgemm_symbolic(7, 1, la._lib.ptr(rowptr), la._lib.ptr(colval), 2, la._lib.ptr(bg_rowptr), la._lib.ptr(bg_cols), ctypes.byref(h)) == 1
+    assert L.hpcla_spgemm_sizes(None, None, None, None) == 1 and L.hpcla_dtb_sizes(None, None, None, None) == 1
+    a = np.zeros(4, dtype=np.int64)
+    out = [np.zeros(2, dtype=np.int64) for _ in range(9)]
+    bad = np.array([1, 4, 3], dtype=np.int64)  # decreasing
+    ok = np.array([1, 2, 3], dtype=np.int64)
+    rc = L.hpcla_repartition_plan(0, 2, la._lib.ptr(bad), la._lib.ptr(ok), *[la._lib.ptr(o) for o in out[:8]], la._lib.ptr(a), la._lib.ptr(out[8]))
+    assert rc == 1 and b"non-decreasing" in L.hpcla_last_error()
+    # a well-formed tiny product, through the plain C ABI
+    colval[1] = 2
+    assert L.hpcla_spgemm_symbolic(la._lib.I32, 1, la._lib.ptr(rowptr), la._lib.ptr(colval), 2, la._lib.ptr(bg_rowptr), la._lib.ptr(bg_cols), ctypes.byref(h)) == 0
+    nnz, ncc, nt = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    assert L.hpcla_spgemm_sizes(h, ctypes.byref(nnz), ctypes.byref(ncc), ctypes.byref(nt)) == 0 and (nnz.value, ncc.value, nt.value) == (2, 2, 2)
+    L.hpcla_spgemm_destroy(h)
