@@ -34,7 +34,26 @@ def load_fixtures():
     return out, raw["plans"]
 
 
+def load_product_fixtures():
+    """Literal inputs of the reference's product tests (sparse*sparse, sparse*dense) with dense-numpy expectations."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_fixtures.json")) as f:
+        raw = json.load(f)
+    out = []
+    for fx in raw.get("products", []):
+        dt = np.complex128 if fx["dtype"] == "c128" else np.float64
+        c = dict(fx)
+        for side in ("A", "B"):
+            if side in c:
+                c[side] = dict(c[side], V=_dec(c[side]["V"], dt).astype(dt))
+        for k in ("Bdense", "C", "CT"):
+            if k in c:
+                c[k] = _dec(c[k], dt).astype(dt)
+        out.append(c)
+    return out
+
+
 FIXTURES, PLAN_TABLES = load_fixtures()
+PRODUCT_FIXTURES = load_product_fixtures()
 
 
 def fixture_matrix(fx):

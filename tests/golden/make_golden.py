@@ -185,9 +185,45 @@ def main():
                       "nzval": [12, 5, 6, 13, 7, 8]},
         },
     }
+    # ---- the callers of the hot path: literal inputs of the reference's product tests ------------------
+    products = []
+    for cplx in (False, True):
+        T = "c128" if cplx else "f64"
+        dt = np.complex128 if cplx else np.float64
+        n = 8
+        # test/test_matrix_multiplication.jl:38-62: tridiagonal A (test_utils.jl:90-100) times a second tridiagonal B
+        IA, JA, VA = tridiagonal(n, cplx)
+        IB = list(range(1, n + 1)) + list(range(1, n)) + list(range(2, n + 1))
+        JB = list(range(1, n + 1)) + list(range(2, n + 1)) + list(range(1, n))
+        VB = [1.5] * n + [0.25] * (n - 1) + [0.25] * (n - 1)
+        if cplx:
+            VB = [complex(a, b) for a, b in zip(VB, [-0.1] * n + [0.1] * (n - 1) + [0.1] * (n - 1))]
+        A, B = dense(IA, JA, VA, n, n, dt), dense(IB, JB, VB, n, n, dt)
+        products.append({"name": f"spgemm_tridiag8_{T}", "kind": "sparse*sparse", "source": "test/test_matrix_multiplication.jl:38-62", "dtype": T,
+                         "A": {"m": n, "n": n, "I": IA, "J": JA, "V": enc(VA)}, "B": {"m": n, "n": n, "I": IB, "J": JB, "V": enc(VB)},
+                         "C": enc(A @ B), "tol": 1e-10})
+        # test/test_matrix_multiplication.jl:65-92: 6x8 times 8x10
+        IA2, JA2 = [1, 2, 3, 4, 5, 6, 1, 2, 3, 4], [1, 2, 3, 4, 5, 6, 7, 8, 1, 2]
+        IB2, JB2 = [1, 2, 3, 4, 5, 6, 7, 8, 1, 3], [1, 2, 3, 4, 5, 6, 7, 8, 9, 10]
+        V2 = [complex(k, 11 - k) for k in range(1, 11)] if cplx else [float(k) for k in range(1, 11)]
+        A2, B2 = dense(IA2, JA2, V2, 6, 8, dt), dense(IB2, JB2, V2, 8, 10, dt)
+        products.append({"name": f"spgemm_6x8x10_{T}", "kind": "sparse*sparse", "source": "test/test_matrix_multiplication.jl:65-92", "dtype": T,
+                         "A": {"m": 6, "n": 8, "I": IA2, "J": JA2, "V": enc(V2)}, "B": {"m": 8, "n": 10, "I": IB2, "J": JB2, "V": enc(V2)},
+                         "C": enc(A2 @ B2), "tol": 1e-10})
+        # test/test_new_operations.jl:46-59, 79-88: A_sparse = S + S^T + 2I times the dense 8x6 B; also transpose(A) * B
+        IS = [1, 2, 3, 4, 5, 6, 7, 8, 1, 2, 3, 4, 5, 6, 7, 8]
+        JS = [1, 2, 3, 4, 5, 6, 7, 8, 2, 3, 4, 5, 6, 7, 8, 1]
+        VS = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]
+        Sd = dense(IS, JS, VS, n, n, dt)
+        Ad = Sd + Sd.T + 2.0 * np.eye(n, dtype=dt)
+        I3, J3 = np.nonzero(Ad)
+        Bd = np.array([[i + j * 0.1 for j in range(1, 7)] for i in range(1, 9)], dtype=dt)
+        products.append({"name": f"spmm_sym8_{T}", "kind": "sparse*dense", "source": "test/test_new_operations.jl:46-59, 79-88", "dtype": T,
+                         "A": {"m": n, "n": n, "I": (I3 + 1).tolist(), "J": (J3 + 1).tolist(), "V": enc(Ad[I3, J3])}, "Bdense": enc(Bd),
+                         "C": enc(Ad @ Bd), "CT": enc(Ad.T @ Bd), "tol": 1e-10})
     with open(os.path.join(HERE, "reference_fixtures.json"), "w") as f:
-        json.dump({"fixtures": fx, "plans": plans}, f, indent=1)
-    print(f"wrote {len(fx)} fixtures")
+        json.dump({"fixtures": fx, "plans": plans, "products": products}, f, indent=1)
+    print(f"wrote {len(fx)} fixtures, {len(products)} product fixtures")
 
 
 if __name__ == "__main__":

@@ -576,3 +576,30 @@ def test_sparse_times_sparse(T, Ti, P):
             assert np.array_equal(vals, o.nzval), "same terms, same order, products rounded separately: the reference's values bit for bit"
             assert np.array_equal(vals2, 2 * o.nzval)
             assert relerr(y, y_ref) <= (1e-4 if T == np.float32 else 1e-12)
+
+
+def test_reference_product_fixtures_on_device():
+    """The reference's own product tests (sparse*sparse, sparse*dense, transpose(sparse)*dense: literal inputs,
+    tests/golden) through the library at 1 and 2 ranks, at the tests' tolerance."""
+    from conftest import PRODUCT_FIXTURES
+
+    for fx in PRODUCT_FIXTURES:
+        T = np.complex128 if fx["dtype"] == "c128" else np.float64
+        A = fixture_matrix(fx["A"])
+        for P, Ti in [(1, np.int64), (2, np.int32)]:
+            def body(rank, bs):
+                b = bs[rank]
+                torch.cuda.set_device(b.torch_device())
+                Am = la.HPCSparseMatrix.from_global(A, b)
+                if fx["kind"] == "sparse*sparse":
+                    C = Am * la.HPCSparseMatrix.from_global(fixture_matrix(fx["B"]), b)
+                    rows = sp.csr_matrix((C.nzval_host(), C.col_indices[C.colval - 1] - 1, C.rowptr - 1), shape=(C.nrows_local, fx["C"].shape[1])).toarray()
+                    return np.concatenate(la.comm_allgather(b.comm, rows), axis=0), None
+                Bm = la.HPCMatrix.from_global(fx["Bdense"], b)
+                return (Am * Bm).to_global(), (la.transpose(Am) * Bm).to_global()
+
+            la.clear_plan_cache()
+            for C, CT in spmd(backends(P, T, Ti), body):
+                assert np.max(np.abs(C - fx["C"])) < fx["tol"], fx["name"]
+                if CT is not None:
+                    assert np.max(np.abs(CT - fx["CT"])) < fx["tol"], fx["name"]

@@ -218,3 +218,22 @@ def test_cg_restatement_converges_on_laplacian():
     b = A @ np.ones(n)
     x, hist = orc.cg(locs, b, 70)
     assert np.linalg.norm(x - 1.0) < 1e-8
+
+
+def test_reference_product_fixtures():
+    """The oracle's restatements of the hot path's callers against the literal inputs of the reference's own product
+    tests (test/test_matrix_multiplication.jl:38-92, test/test_new_operations.jl:46-88) at the tests' tolerance."""
+    from conftest import PRODUCT_FIXTURES, fixture_matrix
+
+    assert len(PRODUCT_FIXTURES) == 6
+    for fx in PRODUCT_FIXTURES:
+        A = fixture_matrix(fx["A"])
+        for P in (1, 2, 3):
+            lA = orc.distribute(A, P)
+            if fx["kind"] == "sparse*sparse":
+                B = fixture_matrix(fx["B"])
+                C = orc.to_global(orc.spgemm(lA, orc.distribute(B, P)), fx["C"].shape).toarray()
+                assert np.max(np.abs(C - fx["C"])) < fx["tol"], fx["name"]
+            else:
+                assert np.max(np.abs(orc.matmat(lA, fx["Bdense"]) - fx["C"])) < fx["tol"], fx["name"]
+                assert np.max(np.abs(orc.matmat(orc.transpose(lA), fx["Bdense"]) - fx["CT"])) < fx["tol"], fx["name"]
