@@ -55,74 +55,79 @@ int symbolic_typed(i64 nrows, const Ti* a_rowptr, const Ti* a_colval, i64 n_rows
     if (nnz_a >= (i64)INT32_MAX || nnz_b >= (i64)INT32_MAX) return fail(HPCLA_ERR_ARG, "hpcla_spgemm_symbolic: operands with 2^31 or more stored entries are not supported");
     P->nrows = nrows;
     P->rowptr.assign((size_t)nrows + 1, 1);
-    std::vector<i64> row_terms((size_t)nrows + 1, 0);
+    // One pass, one sort per row: thread t takes a contiguous block of rows and appends to its own buffers (output
+    // columns, terms per output entry, the term lists); the blocks are then laid end to end.
     const int nt = host_threads(nnz_a * 8);
-    // pass 1: stored entries and terms per row
-    auto pass1 = [&](int t) {
-        std::vector<i64> cols;
-        for (i64 i = t; i < nrows; i += nt) {
-            cols.clear();
-            for (i64 j = (i64)a_rowptr[i] - 1; j < (i64)a_rowptr[i + 1] - 1; ++j) {
-                const i64 g = (i64)a_colval[j] - 1;
-                for (i64 q = bg_rowptr[g] - 1; q < bg_rowptr[g + 1] - 1; ++q) cols.push_back(bg_cols[q]);
-            }
-            row_terms[(size_t)i + 1] = (i64)cols.size();
-            std::sort(cols.begin(), cols.end());
-            P->rowptr[(size_t)i + 1] = (i64)(std::unique(cols.begin(), cols.end()) - cols.begin());
-        }
+    struct Part {
+        std::vector<i64> cols, tcount;  // per output entry: global column, number of terms
+        std::vector<int> ia, ib;
     };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(pass1, t);
-        pass1(0);
-        for (auto& x : th) x.join();
-    }
-    for (i64 i = 0; i < nrows; ++i) {
-        P->rowptr[(size_t)i + 1] += P->rowptr[(size_t)i];
-        row_terms[(size_t)i + 1] += row_terms[(size_t)i];
-    }
-    P->nnz = P->rowptr[(size_t)nrows] - 1;
-    P->nterms = row_terms[(size_t)nrows];
-    if (P->nterms >= (i64)1 << 40) return fail(HPCLA_ERR_NOMEM, "hpcla_spgemm_symbolic: %lld product terms", (long long)P->nterms);
-    P->cols_global.resize((size_t)P->nnz);
-    P->term_ptr.assign((size_t)P->nnz + 1, 0);
-    P->ia.resize((size_t)P->nterms);
-    P->ib.resize((size_t)P->nterms);
-    // pass 2: per row, the terms sorted by output column, stable in k (A's entries ascend in k, so does the collection order)
-    auto pass2 = [&](int t) {
+    std::vector<Part> parts((size_t)nt);
+    auto work = [&](int t) {
+        Part& W = parts[(size_t)t];
+        const i64 lo = nrows * t / nt, hi = nrows * (t + 1) / nt;
         std::vector<Triple> tr;
-        for (i64 i = t; i < nrows; i += nt) {
+        for (i64 i = lo; i < hi; ++i) {
             tr.clear();
             for (i64 j = (i64)a_rowptr[i] - 1; j < (i64)a_rowptr[i + 1] - 1; ++j) {
                 const i64 g = (i64)a_colval[j] - 1;
                 for (i64 q = bg_rowptr[g] - 1; q < bg_rowptr[g + 1] - 1; ++q) tr.push_back(Triple{bg_cols[q], (int)j, (int)q});
             }
+            // by output column, stable in k: A's entries ascend in k, so does the collection order
             std::stable_sort(tr.begin(), tr.end(), [](const Triple& x, const Triple& y) { return x.c < y.c; });
-            i64 d = P->rowptr[(size_t)i] - 1 - 1;  // output entry before the row's first
-            i64 tpos = row_terms[(size_t)i];
+            i64 nout = 0;
             for (size_t u = 0; u < tr.size(); ++u) {
                 if (u == 0 || tr[u].c != tr[u - 1].c) {
-                    ++d;
-                    P->cols_global[(size_t)d] = tr[u].c;
-                    P->term_ptr[(size_t)d] = tpos;
+                    W.cols.push_back(tr[u].c);
+                    W.tcount.push_back(0);
+                    ++nout;
                 }
-                P->ia[(size_t)tpos] = tr[u].ia;
-                P->ib[(size_t)tpos] = tr[u].ib;
-                ++tpos;
+                W.tcount.back() += 1;
+                W.ia.push_back(tr[u].ia);
+                W.ib.push_back(tr[u].ib);
             }
+            P->rowptr[(size_t)i + 1] = nout;  // row counts for now
         }
     };
     {
         std::vector<std::thread> th;
-        for (int t = 1; t < nt; ++t) th.emplace_back(pass2, t);
-        pass2(0);
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
         for (auto& x : th) x.join();
     }
-    P->term_ptr[(size_t)P->nnz] = P->nterms;
-    // col_indices = unique!(sort(global columns)) (src/sparse.jl:1023)
-    P->col_indices = P->cols_global;
-    std::sort(P->col_indices.begin(), P->col_indices.end());
-    P->col_indices.erase(std::unique(P->col_indices.begin(), P->col_indices.end()), P->col_indices.end());
+    for (i64 i = 0; i < nrows; ++i) P->rowptr[(size_t)i + 1] += P->rowptr[(size_t)i];
+    P->nnz = P->rowptr[(size_t)nrows] - 1;
+    P->nterms = 0;
+    for (const Part& W : parts) P->nterms += (i64)W.ia.size();
+    if (P->nterms >= (i64)1 << 40) return fail(HPCLA_ERR_NOMEM, "hpcla_spgemm_symbolic: %lld product terms", (long long)P->nterms);
+    P->cols_global.resize((size_t)P->nnz);
+    P->term_ptr.assign((size_t)P->nnz + 1, 0);
+    P->ia.resize((size_t)P->nterms);
+    P->ib.resize((size_t)P->nterms);
+    {
+        i64 d = 0, tpos = 0;
+        for (Part& W : parts) {
+            std::copy(W.cols.begin(), W.cols.end(), P->cols_global.begin() + d);
+            for (size_t u = 0; u < W.tcount.size(); ++u) {
+                P->term_ptr[(size_t)d + u] = tpos;
+                tpos += W.tcount[u];
+            }
+            std::copy(W.ia.begin(), W.ia.end(), P->ia.begin() + (tpos - (i64)W.ia.size()));
+            std::copy(W.ib.begin(), W.ib.end(), P->ib.begin() + (tpos - (i64)W.ib.size()));
+            d += (i64)W.cols.size();
+            Part().cols.swap(W.cols), Part().tcount.swap(W.tcount), Part().ia.swap(W.ia), Part().ib.swap(W.ib);  // release as we go
+        }
+        P->term_ptr[(size_t)P->nnz] = tpos;
+    }
+    // col_indices = unique!(sort(global columns)) (src/sparse.jl:1023): a presence map over the columns in use
+    if (P->nnz > 0) {
+        i64 cmax = 0;
+        for (i64 c : P->cols_global) cmax = std::max(cmax, c);
+        std::vector<unsigned char> seen((size_t)cmax + 1, 0);
+        for (i64 c : P->cols_global) seen[(size_t)c] = 1;
+        for (i64 c = 1; c <= cmax; ++c)
+            if (seen[(size_t)c]) P->col_indices.push_back(c);
+    }
     P->ncc = (i64)P->col_indices.size();
     return HPCLA_OK;
 }
@@ -186,8 +191,11 @@ extern "C" int hpcla_spgemm_structure(const hpcla_spgemm* P, int itype, void* ro
         if (itype == HPCLA_I32) ((int32_t*)rowptr_out)[i] = (int32_t)P->rowptr[(size_t)i];
         else ((int64_t*)rowptr_out)[i] = P->rowptr[(size_t)i];
     }
-    for (i64 d = 0; d < P->nnz; ++d) {  // compress: position in col_indices (src/sparse.jl:1026-1034)
-        const i64 local = (i64)(std::lower_bound(P->col_indices.begin(), P->col_indices.end(), P->cols_global[(size_t)d]) - P->col_indices.begin()) + 1;
+    // compress_map[global column] = position in col_indices (src/sparse.jl:1026-1034)
+    std::vector<i64> compress_map(P->col_indices.empty() ? 1 : (size_t)P->col_indices.back() + 1, 0);
+    for (size_t k = 0; k < P->col_indices.size(); ++k) compress_map[(size_t)P->col_indices[k]] = (i64)k + 1;
+    for (i64 d = 0; d < P->nnz; ++d) {
+        const i64 local = compress_map[(size_t)P->cols_global[(size_t)d]];
         if (itype == HPCLA_I32) ((int32_t*)colval_out)[d] = (int32_t)local;
         else ((int64_t*)colval_out)[d] = local;
     }
