@@ -160,13 +160,14 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle's restatement of the reference's distributed A*x, one worker thread per "MPI rank"
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_baseline_run(spec: dict, reps: int, warmup: int, budget_rows: int = 2_200_000):
+def cpu_baseline_run(spec: dict, reps: int, warmup: int, budget_rows: int = 2_200_000, workers: int = 0):
     """Bounded sample: the same stencil on a slab with the workload's plane size but fewer planes (about `budget_rows`
     rows), one worker per host core.  Returns (median seconds, flops, bytes, workers, sample description)."""
     import hpcla_b200 as la
     from oracle import oracle as orc
 
-    workers = os.cpu_count() or 1
+    # one worker per host core; BASELINE.json quotes config 1 (2-D Laplacian) on `mpiexec -n 4`: 4 workers there
+    workers = workers or (4 if spec["kind"] == 0 else (os.cpu_count() or 1))
     kind, (nx, ny, nz), T, Ti = spec["kind"], spec["grid"], spec["T"], spec["Ti"]
     if kind == 3:
         n = min(nx, budget_rows)
@@ -201,7 +202,7 @@ def run_reference_arm(args, spec):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t, fl, bts, workers, desc = cpu_baseline_run(spec, reps=max(args.steps, 1), warmup=max(args.warmup, 1))
+    t, fl, bts, workers, desc = cpu_baseline_run(spec, reps=max(args.steps, 1), warmup=max(args.warmup, 1), workers=args.cpu_workers)
     val = fl / t / 1e9
     line = {
         "impl": "reference", "metric": "spmv_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -437,7 +438,7 @@ def run_b200_arm(args, spec):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t, fl, bts, workers, desc = cpu_baseline_run(spec, reps=7, warmup=1)
+        t, fl, bts, workers, desc = cpu_baseline_run(spec, reps=7, warmup=1, workers=args.cpu_workers)
         cpu = {"value": fl / t / 1e9, "unit": "GFLOP/s", "cores": workers, "kind": "port", "sample": desc, "achieved_gbs": bts / t / 1e9}
 
     if rank == 0:
@@ -465,6 +466,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-workers", type=int, default=0, help="worker threads of the CPU arm (0 = one per host core; 4 for the 2-D Laplacian, as BASELINE.json)")
     args = ap.parse_args()
     spec = workload_spec(args.workload, args.gpus)
     if args.impl == "reference":
