@@ -1,15 +1,41 @@
-// synth.cpp — deterministic synthetic matrices and vectors (see include/hpcla_synth.h).
+// hpcla_synth.cpp — deterministic synthetic matrices and vectors (see include/hpcla_synth.h).
+// Its own small host-only library (libhpcla_synth.so, g++): the tests, bench.py and the CPU reference arm all draw
+// their inputs from it, and the reference arm must not map the product library to do so.
+#include <algorithm>
 #include <cmath>
+#include <cstdarg>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
-#include "../../include/hpcla_synth.h"
-#include "common.h"
+#include "../include/hpcla_synth.h"
 
-using namespace hpcla;
+typedef int64_t i64;
+enum { HPCLA_OK = 0, HPCLA_ERR_ARG = 1 };                  // status values as in include/hpcla_b200.h
+enum { HPCLA_F32 = 0, HPCLA_F64 = 1, HPCLA_C128 = 2, HPCLA_I32 = 0, HPCLA_I64 = 1 };  // type codes as in include/hpcla_b200.h
 
 namespace {
+thread_local std::string g_error;
+thread_local int g_max_threads = 0;  // 0: one per hardware thread (at most 32); hpcla_synth_set_threads
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+int host_threads(i64 work_items) {
+    if (work_items < (i64)1 << 20) return 1;
+    if (g_max_threads > 0) return g_max_threads;
+    unsigned hc = std::thread::hardware_concurrency();
+    int t = hc ? (int)hc : 4;
+    return t > 32 ? 32 : t;
+}
+
 inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;
     x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -145,6 +171,9 @@ int powerlaw_fill_typed(i64 n, uint64_t seed, i64 max_len, i64 rb, i64 re, Ti* r
     return HPCLA_OK;
 }
 }  // namespace
+
+extern "C" const char* hpcla_synth_last_error(void) { return g_error.c_str(); }
+extern "C" void hpcla_synth_set_threads(int n) { g_max_threads = n < 0 ? 0 : n; }
 
 extern "C" int64_t hpcla_synth_stencil_rows(int kind, int64_t nx, int64_t ny, int64_t nz) { return kind == HPCLA_SYNTH_LAPLACE2D_5PT ? nx * ny : nx * ny * nz; }
 

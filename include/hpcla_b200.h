@@ -61,6 +61,13 @@ int hpcla_ctx_adopt_nccl(hpcla_ctx* ctx, void* nccl_comm);
 int hpcla_ctx_form_group(hpcla_ctx* const* ctxs, int n);
 int hpcla_ctx_sync(hpcla_ctx* ctx);
 void hpcla_ctx_destroy(hpcla_ctx* ctx);
+/* Pinned host memory for the staged multiply (hpcla_spmv_run_staged), allocated and first-touched on the CPUs the GPU's
+ * PCIe root is attached to (sysfs local_cpulist), so that on a multi-socket host the H2D / D2H copies stay on the GPU's
+ * own NUMA node.  The host-side counterpart of the reference's `Array(x.v)` / `copyto!` staging buffers
+ * (src/vectors.jl:423, 460), which live wherever Julia's allocator put them.  numa_node_out (may be NULL): the node
+ * read from sysfs, or -1.  Falls back to a plain pinned allocation when the topology cannot be read. */
+int hpcla_host_alloc(hpcla_ctx* ctx, int64_t bytes, void** out, int* numa_node_out);
+int hpcla_host_free(hpcla_ctx* ctx, void* p);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Host-side structure (pure functions, no device).
@@ -139,8 +146,13 @@ void hpcla_dtb_destroy(hpcla_dtb* t);
  * Device objects.
  * ------------------------------------------------------------------------------------------------------------- */
 /* Device view of A: borrows A.rowptr_target / A.colval_target / A.nzval (src/sparse.jl:334-335, 519-520), 1-based
- * contents, unchanged.  Builds the row-tile table used by the kernels (no copy of the matrix is made; in-place value
- * writes to A.nzval — src/indexing.jl:932-982 — are seen by the next multiply). */
+ * contents, unchanged, after one validation pass (rowptr[1] == 1, non-decreasing, rowptr[end] == nnz + 1,
+ * 1 <= colval <= ncols_compressed; HPCLA_ERR_ARG otherwise).  A.nzval is always read in place, so in-place value writes —
+ * src/indexing.jl:932-982 — are seen by the next multiply.  Library-owned STRUCTURE derived from rowptr / colval is
+ * kept beside the matrix: the row-tile table, re-blocked 16-bit row offsets per tile (direct row walk), per (matrix,
+ * plan) the x runs and 16-bit column positions of the interior tiles (compact row walk), and for irregular matrices one
+ * row-start bit per stored entry (nnz-split kernel).  A structural change needs a new handle, exactly as it drops
+ * A.structural_hash and the cached plans in the reference (src/indexing.jl:1291-1294). */
 int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nrows_local, int64_t ncols_compressed, int64_t nnz,
                      const void* d_rowptr, const void* d_colval, const void* d_nzval, hpcla_csr** out);
 /* query: number of row tiles, rows longer than the split threshold, and the lanes per row of the row-walk kernel
@@ -167,6 +179,16 @@ int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
  * once).  Equivalent to copy(h_x -> d_x); hpcla_spmv_run(op, d_x, d_y); copy(d_y -> h_y).  h_x / h_y should be pinned.
  * Enqueue only: h_y is complete once `stream` has been synchronised.  NCCL world or nranks == 1. */
 int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x, void* d_y, void* h_y, void* stream);
+/* One multiply as a CUDA graph bound to fixed x.v / y.v (NCCL world or a single rank): capture (re)builds it — the
+ * event choreography between the caller's stream and the halo stream becomes graph dependencies, the grouped
+ * ncclSend/ncclRecv a captured node — and launch replays it with one driver call.  For the latency-bound regime
+ * (strong scaling: tens of microseconds of kernel per step against ~10 driver calls). */
+int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
+int hpcla_spmv_graph_launch(hpcla_spmv* op, void* stream);
+/* Timeline of the most recent multiply, for operators created with HPCLA_TIMELINE=1 in the environment: milliseconds
+ * from "x ready on the caller's stream" to the end of [0] the halo exchange, [1] the boundary tiles (both on the halo
+ * stream), [2] the interior tiles, [3] the whole call (caller's stream); -1 where a step does not exist.  Blocks. */
+int hpcla_spmv_timeline(hpcla_spmv* op, double* ms4_out);
 /* Single-process world: call begin on every rank, then finish on every rank. */
 int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
 int hpcla_spmv_finish(hpcla_spmv* op);
@@ -188,6 +210,9 @@ int hpcla_spmv_gather_finish(hpcla_spmv* op);
 /* introspection for tests/benchmarks: counts of interior and boundary tiles, whether x.v is read in place */
 int hpcla_spmv_info(const hpcla_spmv* op, int64_t* n_interior_tiles, int64_t* n_boundary_tiles, int* x_in_place,
                     int* sends_contiguous);
+/* which kernel takes what: out6 = {row-walk tiles interior, boundary; general tiles interior, boundary; compact row-walk
+ * tiles (interior); chunks of the nnz-split kernel (irregular matrices: it then takes every stored entry)} */
+int hpcla_spmv_tile_lists(const hpcla_spmv* op, int64_t* out6);
 /* kernel launches enqueued by this operator so far (bench.py's gpu_launches) */
 int64_t hpcla_spmv_launch_count(const hpcla_spmv* op);
 void hpcla_spmv_destroy(hpcla_spmv* op);

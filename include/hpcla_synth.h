@@ -1,7 +1,9 @@
 /* hpcla_synth.h — deterministic synthetic inputs shared by the tests, the benchmark and the CPU baseline
- * (SURVEY.md §8d).  Host-only helpers exported by libhpcla_b200.so next to the backend ABI; they are not part of
- * the interface the reference would bind (the reference builds its matrices with SparseArrays, e.g.
- * tools/benchmark_vs_petsc.jl:42-49 for the 2-D Laplacian).
+ * (SURVEY.md §8d).  Host-only helpers in a library of their own, hpcla_synth/libhpcla_synth.so (g++, no CUDA), so that
+ * the CPU reference arm can draw the same inputs without mapping the product library; they are not part of the
+ * interface the reference would bind (the reference builds its matrices with SparseArrays, e.g.
+ * tools/benchmark_vs_petsc.jl:42-49 for the 2-D Laplacian).  Type codes: dtype 0 Float32, 1 Float64, 2 ComplexF64;
+ * itype 0 Int32, 1 Int64 (as in hpcla_b200.h).  Every int-returning function returns 0 on success.
  *
  * Every generator emits the rows [row_begin, row_end) (0-based global rows) of the matrix as the input of
  * HPCSparseMatrix_local (src/sparse.jl:454): 1-based rowptr (Ti), 1-based GLOBAL columns ascending within a row (Ti),
@@ -33,6 +35,12 @@ int hpcla_synth_powerlaw_fill(int64_t n, uint64_t seed, int64_t max_len, int dty
 
 /* x[g] = 2u(g) - 1 for g in [begin, end) (0-based); ComplexF64 adds an independent imaginary part. */
 int hpcla_synth_vector(int dtype, uint64_t seed, int64_t begin, int64_t end, void* out);
+
+/* message of the last failure on the calling thread */
+const char* hpcla_synth_last_error(void);
+/* worker threads the generators may use on the calling thread's behalf (0 = one per hardware thread, at most 32);
+ * the CPU reference arm sets 1 inside each of its workers so that a worker first-touches its own arrays */
+void hpcla_synth_set_threads(int n);
 
 #ifdef __cplusplus
 }

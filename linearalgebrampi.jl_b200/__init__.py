@@ -17,7 +17,7 @@ from .vectors import (  # noqa: F401
 )
 from .sparse import (  # noqa: F401
     HPCSparseMatrix, Transpose, VectorPlan, build_vector_plan, cache_sizes, cg, clear_plan_cache, compute_structural_hash,
-    execute_plan, get_vector_plan, materialize_transpose, matvec, mul, mul_staged, spmv_info, to_backend, transpose, transpose_matvec,
+    execute_plan, get_vector_plan, host_buffer, materialize_transpose, matvec, mul, mul_graph, mul_staged, spmv_info, spmv_timeline, to_backend, transpose, transpose_matvec,
     vec_adjoint_mul, vec_transpose_mul,
 )
 from .dense import HPCMatrix, spmm  # noqa: F401

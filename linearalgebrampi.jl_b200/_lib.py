@@ -1,4 +1,4 @@
-"""ctypes binding of libhpcla_b200.so (include/hpcla_b200.h, include/hpcla_synth.h).
+"""ctypes binding of libhpcla_b200.so (include/hpcla_b200.h).
 
 The product path has no fallback: if the shared library is missing this module raises, it never substitutes a
 CPU implementation (the CPU oracle under oracle/ is test infrastructure and is never imported from here).
@@ -53,6 +53,8 @@ SIGNATURES = {
     "hpcla_ctx_form_group": (_i, [_vp, _i]),
     "hpcla_ctx_sync": (_i, [_vp]),
     "hpcla_ctx_destroy": (None, [_vp]),
+    "hpcla_host_alloc": (_i, [_vp, _i64, _vp, _vp]),
+    "hpcla_host_free": (_i, [_vp, _vp]),
     "hpcla_uniform_partition": (_i, [_i64, _i, _vp]),
     "hpcla_compress_columns": (_i, [_i, _i64, _vp, _i64, _vp, _vp, _vp]),
     "hpcla_plan_begin": (_i, [_i, _i, _vp, _i64, _vp, _vp]),
@@ -81,6 +83,9 @@ SIGNATURES = {
     "hpcla_spmv_create": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hpcla_spmv_run": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_run_staged": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "hpcla_spmv_graph_capture": (_i, [_vp, _vp, _vp, _vp]),
+    "hpcla_spmv_graph_launch": (_i, [_vp, _vp]),
+    "hpcla_spmv_timeline": (_i, [_vp, _vp]),
     "hpcla_spmv_begin": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_finish": (_i, [_vp]),
     "hpcla_spmm_run": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),
@@ -89,6 +94,7 @@ SIGNATURES = {
     "hpcla_spmv_gather": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_gather_finish": (_i, [_vp]),
     "hpcla_spmv_info": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "hpcla_spmv_tile_lists": (_i, [_vp, _vp]),
     "hpcla_spmv_launch_count": (_i64, [_vp]),
     "hpcla_spmv_destroy": (None, [_vp]),
     "hpcla_spgemm_symbolic": (_i, [_i, _i64, _vp, _vp, _i64, _vp, _vp, _vp]),
@@ -103,13 +109,6 @@ SIGNATURES = {
     "hpcla_cg": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "hpcla_repartition_plan": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hpcla_repartition_run": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    # include/hpcla_synth.h
-    "hpcla_synth_stencil_rows": (_i64, [_i, _i64, _i64, _i64]),
-    "hpcla_synth_stencil_nnz": (_i64, [_i, _i64, _i64, _i64, _i64, _i64]),
-    "hpcla_synth_stencil_fill": (_i, [_i, _i64, _i64, _i64, _i, _i, _i64, _i64, _vp, _vp, _vp]),
-    "hpcla_synth_powerlaw_nnz": (_i64, [_i64, _u64, _i64, _i64, _i64]),
-    "hpcla_synth_powerlaw_fill": (_i, [_i64, _u64, _i64, _i, _i, _i64, _i64, _vp, _vp, _vp]),
-    "hpcla_synth_vector": (_i, [_i, _u64, _i64, _i64, _vp]),
 }
 
 

@@ -95,12 +95,16 @@ class CommSerial(AbstractComm):
 class CommMPI(AbstractComm):
     """A torch.distributed process group in the role of `CommMPI(comm::MPI.Comm)` (src/backends.jl:73-75)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, nccl_comm: Optional[int] = None):
+        """nccl_comm: address of an ncclComm_t created by the caller for this group — the communicator the reference
+        already caches per MPI communicator (ext/HPCLinearAlgebraCUDAExt.jl:411-443); adopted, not owned, by the
+        library (hpcla_ctx_adopt_nccl).  None: the library bootstraps its own (hpcla_ctx_init_nccl)."""
         import torch.distributed as dist
 
         if not dist.is_initialized():
             raise RuntimeError("CommMPI needs torch.distributed.init_process_group() first (the reference needs MPI.Init())")
         self.group = group
+        self.nccl_comm = nccl_comm
         self.uid = next(_comm_uid)
         self._ctxs = {}
         self._dist = dist
@@ -371,6 +375,10 @@ def _device_context(b: HPCBackend) -> DeviceContext:
     _lib.check(L.hpcla_ctx_create(dev, rank, size, ctypes.byref(h)))
     if isinstance(comm, CommSerial) or size == 1:
         world = "single"
+    elif isinstance(comm, CommMPI) and comm.nccl_comm:
+        torch.cuda.set_device(dev)
+        _lib.check(L.hpcla_ctx_adopt_nccl(h, comm.nccl_comm))  # the caller's cached communicator (ext:411-443)
+        world = "nccl"
     elif isinstance(comm, CommMPI):
         # NCCL bootstrap as ext/HPCLinearAlgebraCUDAExt.jl:411-443: rank 0 makes the id, the host comm broadcasts it
         ident = np.zeros(128, dtype=np.uint8)

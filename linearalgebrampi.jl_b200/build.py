@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhpcla_b200.so")
-SOURCES = ["host.cpp", "synth.cpp", "kernels.cu", "spmm.cu", "transpose.cu", "spgemm.cu", "context.cu"]
-HEADERS = ["common.h", "device.h", "device_common.cuh", os.path.join("..", "..", "include", "hpcla_b200.h"), os.path.join("..", "..", "include", "hpcla_synth.h")]
+SOURCES = ["host.cpp", "kernels.cu", "compact.cu", "flat.cu", "spmm.cu", "transpose.cu", "spgemm.cu", "context.cu"]
+HEADERS = ["common.h", "device.h", "device_common.cuh", os.path.join("..", "..", "include", "hpcla_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -5,10 +5,14 @@
 // `gathered` per call) and the launch in Base.:*(A, x) / mul! (src/sparse.jl:2096-2128, 2019-2037).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sched.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
@@ -81,6 +85,23 @@ NcclApi* nccl_api() {
         if (_r != ncclSuccess) return fail(HPCLA_ERR_NCCL, "%s failed: %s", #expr, nccl_api()->GetErrorString(_r)); \
     } while (0)
 
+// Inside ncclGroupStart .. ncclGroupEnd: a failed call closes the group before the error is returned, so that later
+// NCCL calls of this thread are not queued behind a group that never ends.
+#define NCCL_TRY_IN_GROUP(expr)                                                                                    \
+    do {                                                                                                           \
+        ncclResult_t _r = (expr);                                                                                  \
+        if (_r != ncclSuccess) {                                                                                   \
+            nccl_api()->GroupEnd();                                                                                \
+            return fail(HPCLA_ERR_NCCL, "%s failed: %s", #expr, nccl_api()->GetErrorString(_r));                   \
+        }                                                                                                          \
+    } while (0)
+
+// NVTX ranges around the entry points that enqueue work: no-ops unless a tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 struct hpcla_group {
     std::mutex mu;  // rank-threads register and look up operators concurrently
@@ -118,6 +139,8 @@ struct hpcla_csr {
     i64 nlong = 0, nchunks = 0;
     i64 *d_long_rows = nullptr, *d_chunk_ptr = nullptr;
     void* d_partials = nullptr;
+    FlatData flat;        // irregular matrices: the nnz-split multiply (flat.cu); n_chunks == 0 otherwise
+    bool flat_keep_x = false;  // gather x with an L2 evict-last hint (HPCLA_FLAT_KEEP_X)
 };
 
 struct Seg {
@@ -134,7 +157,7 @@ struct HostPipe {
     bool usable = false;
     int nb = 0;
     std::vector<i64> row_at;     // [nb+1] first local row of each block
-    std::vector<int> pos[2][2];  // [nb+1] positions of the block boundaries in each tile list
+    std::vector<int> pos[3][2];  // [nb+1] positions of the block boundaries in each tile list
     std::vector<int> in_chunk;   // [nb] the x chunk that must have landed before the block runs (-1: none)
     std::vector<char> late;      // [nb] y slice complete only after the boundary tiles / split long rows
     std::vector<i64> xchunk;     // [nb+1] element offsets of the x chunks
@@ -160,11 +183,16 @@ struct hpcla_spmv {
     void* d_sendbuf = nullptr;
     i64* d_send_idx = nullptr;                              // concatenated send_indices (all peers)
     i64 *d_local_src = nullptr, *d_local_dst = nullptr;     // only when needed (fallback / gather hook)
-    TileRec* d_list[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [kernel class - 1][0 interior, 1 boundary]
-    int n_list[2][2] = {{0, 0}, {0, 0}};
-    std::vector<int> h_list[2][2];  // host copies (block boundaries of the staged multiply)
+    // tile lists [class][0 interior, 1 boundary]; class 0: row walk, 1: general kernel, 2: row walk on compact tiles
+    // (interior only: the tiles of class 0 for which compact data could be built)
+    TileRec* d_list[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    int n_list[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    std::vector<int> h_list[3][2];  // host copies (block boundaries of the staged multiply)
     // every list as runs of consecutive tiles, found once: {first position in the list, first tile}, ascending
-    std::vector<std::pair<int, int>> runs[2][2];
+    std::vector<std::pair<int, int>> runs[3][2];
+    // compact tiles (compact.cu): headers and 16-bit positions, by position in list [2][0]
+    CompactShape csh{};
+    unsigned char *d_chdr = nullptr, *d_cpos = nullptr;
     struct HostPipe* pipe = nullptr;
     // fused dot(x, A x) for CG: one partial per row-walk CTA, interior list first, then boundary list
     double* d_dot_partials = nullptr;
@@ -185,6 +213,24 @@ struct hpcla_spmv {
     int mm_ncols = 0;
     std::atomic<long long> epoch{0};  // exchanges begun (a peer's finish checks that I have begun the matching one)
     i64 launches = 0;
+    double* d_cg_scalars = nullptr;  // hpcla_cg: rr history + p.q (device)
+    int cg_cap = 0;
+    std::vector<double> cg_host;
+    cudaEvent_t ev_last = nullptr;  // end of the most recent call on the caller's stream (what destroy waits for)
+    // HPCLA_TIMELINE=1: timing events of the most recent multiply (hpcla_spmv_timeline)
+    bool timeline = false;
+    cudaEvent_t tl[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // x ready, exchange done, boundary done, interior done, end
+    bool tl_rec[5] = {false, false, false, false, false};
+    // CUDA graph of one multiply bound to fixed x / y (hpcla_spmv_graph_*)
+    cudaGraphExec_t cg_graph = nullptr;  // HPCLA_CG_GRAPH=1: the whole hpcla_cg loop, keyed by its buffers and length
+    const void *cg_key_b = nullptr, *cg_key_x = nullptr, *cg_key_w = nullptr;
+    int cg_key_iters = -1;
+    bool cg_key_fused = false;
+    i64 cg_graph_launches = 0;
+    cudaGraphExec_t graph = nullptr;
+    const void* graph_x = nullptr;
+    void* graph_y = nullptr;
+    i64 graph_launches = 0;
 };
 
 // Handles under construction: destroyed on every early return, released on success.
@@ -306,6 +352,72 @@ extern "C" int hpcla_ctx_form_group(hpcla_ctx* const* ctxs, int n) {
     return HPCLA_OK;
 }
 
+// Pinned host memory placed next to the GPU: the calling thread is moved onto the CPUs the GPU's PCIe root is attached
+// to (sysfs local_cpulist) while cudaHostAlloc allocates and touches the pages, so that on a multi-socket host the
+// staged multiply's H2D / D2H copies do not cross the socket interconnect.  Falls back to a plain pinned allocation
+// when the topology cannot be read.
+static bool parse_cpulist(const char* s, cpu_set_t* set) {
+    CPU_ZERO(set);
+    int n = 0;
+    while (*s) {
+        char* end = nullptr;
+        long a = strtol(s, &end, 10);
+        if (end == s) break;
+        long b = a;
+        s = end;
+        if (*s == '-') {
+            b = strtol(s + 1, &end, 10);
+            s = end;
+        }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET((int)c, set), ++n;
+        if (*s == ',') ++s;
+        else break;
+    }
+    return n > 0;
+}
+
+extern "C" int hpcla_host_alloc(hpcla_ctx* ctx, int64_t bytes, void** out, int* numa_node_out) {
+    if (!ctx || !out || bytes < 0) return fail(HPCLA_ERR_ARG, "hpcla_host_alloc: bad arguments");
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    if (numa_node_out) *numa_node_out = -1;
+    char busid[64] = {0};
+    cpu_set_t old_set, gpu_set;
+    bool moved = false;
+    if (cudaDeviceGetPCIBusId(busid, sizeof busid, ctx->device) == cudaSuccess && sched_getaffinity(0, sizeof old_set, &old_set) == 0) {
+        for (char* c = busid; *c; ++c) *c = (char)tolower(*c);
+        char path[160], buf[4096];
+        snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", busid);
+        if (FILE* f = fopen(path, "r")) {
+            if (fgets(buf, sizeof buf, f) && parse_cpulist(buf, &gpu_set)) {
+                CPU_AND(&gpu_set, &gpu_set, &old_set);  // never leave the CPUs this process is allowed on
+                if (CPU_COUNT(&gpu_set) > 0 && sched_setaffinity(0, sizeof gpu_set, &gpu_set) == 0) moved = true;
+            }
+            fclose(f);
+        }
+        snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", busid);
+        if (FILE* f = fopen(path, "r")) {
+            int node = -1;
+            if (fscanf(f, "%d", &node) == 1 && numa_node_out) *numa_node_out = node;
+            fclose(f);
+        }
+    }
+    cudaError_t e = cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocDefault);
+    if (e == cudaSuccess && bytes > 0) std::memset(*out, 0, (size_t)bytes);  // first touch from the GPU's own CPUs
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (e != cudaSuccess) return fail(HPCLA_ERR_CUDA, "hpcla_host_alloc: cudaHostAlloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_host_free(hpcla_ctx* ctx, void* p) {
+    if (!ctx) return fail(HPCLA_ERR_ARG, "hpcla_host_free: null");
+    if (!p) return HPCLA_OK;
+    int rc = set_device(ctx);
+    if (rc) return rc;
+    CU_TRY(cudaFreeHost(p));
+    return HPCLA_OK;
+}
+
 extern "C" int hpcla_ctx_sync(hpcla_ctx* ctx) {
     if (!ctx) return fail(HPCLA_ERR_ARG, "hpcla_ctx_sync: null");
     int rc = set_device(ctx);
@@ -352,8 +464,8 @@ int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, 
     NCCL_TRY(api->GroupStart());
     for (int q = 0; q < ctx->nranks; ++q) {
         if (q == me) continue;
-        if (send_bytes[q] > 0) NCCL_TRY(api->Send((const char*)d_send + send_off[q], (size_t)send_bytes[q], ncclChar, q, ctx->comm, stream));
-        if (recv_bytes[q] > 0) NCCL_TRY(api->Recv((char*)d_recv + recv_off[q], (size_t)recv_bytes[q], ncclChar, q, ctx->comm, stream));
+        if (send_bytes[q] > 0) NCCL_TRY_IN_GROUP(api->Send((const char*)d_send + send_off[q], (size_t)send_bytes[q], ncclChar, q, ctx->comm, stream));
+        if (recv_bytes[q] > 0) NCCL_TRY_IN_GROUP(api->Recv((char*)d_recv + recv_off[q], (size_t)recv_bytes[q], ncclChar, q, ctx->comm, stream));
     }
     NCCL_TRY(api->GroupEnd());
     return HPCLA_OK;
@@ -385,13 +497,29 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     A->d_colval = d_colval;
     A->d_nzval = d_nzval;
     cudaStream_t st = ctx->halo_stream;
+    // The arrays are borrowed as they are: check once that they describe a CSR matrix, so that a wrong row pointer or
+    // column fails here and not as an out-of-range bulk copy or gather on the device (HPCLA_VALIDATE=0 skips the pass).
+    {
+        const char* e = getenv("HPCLA_VALIDATE");
+        if (!(e && e[0] == '0')) {
+            unsigned* d_bad = nullptr;
+            unsigned bad = 0;
+            CU_TRY(cudaMalloc(&d_bad, sizeof(unsigned)));
+            CU_TRY(cudaMemsetAsync(d_bad, 0, sizeof(unsigned), st));
+            CU_TRY(launch_validate_csr(itype, d_rowptr, d_colval, nrows, nnz, ncc, d_bad, st));
+            CU_TRY(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            cudaFree(d_bad);
+            if (bad) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: the arrays are not a valid 1-based CSR view (%u violations of: rowptr[1] == 1, rowptr non-decreasing, rowptr[end] == nnz + 1, 1 <= colval <= ncols_compressed)", bad);
+        }
+    }
     // Tile shape from the mean row length, then the kernel class of every tile (row walk for balanced, fully staged
     // tiles; general otherwise).  A matrix whose tiles are mostly general is re-tiled with the general kernel's own
     // shape.  Tuning hooks: HPCLA_LANES, HPCLA_TILE_WINDOW, HPCLA_SPMV_KIND=general|rowwalk.
     int lanes_override = 0, window_override = 0, kind = 0;
     if (const char* e = getenv("HPCLA_LANES")) lanes_override = atoi(e);
     if (const char* e = getenv("HPCLA_TILE_WINDOW")) window_override = atoi(e);
-    if (const char* e = getenv("HPCLA_SPMV_KIND")) kind = (e[0] == 'g') ? 2 : (e[0] == 'r') ? 1 : 0;
+    if (const char* e = getenv("HPCLA_SPMV_KIND")) kind = (e[0] == 'g') ? 2 : (e[0] == 'r') ? 1 : (e[0] == 'f') ? 3 : 0;
     int balance_pct = 50;  // a tile goes to the row walk when its mean row length is at least this share of its longest row
     if (const char* e = getenv("HPCLA_BALANCE_PCT")) balance_pct = std::max(0, std::min(100, atoi(e)));
     // typical row length: the most common one (a window of whole typical rows keeps tiles row-aligned), else the mean
@@ -413,7 +541,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
     A->long_threshold = 16384;
     A->chunk_nnz = 16384;
     for (int pass = 0; pass < 2; ++pass) {
-        const bool irregular = (pass == 1) || kind == 2;
+        const bool irregular = (pass == 1) || kind == 2 || kind == 3;
         A->shape = tile_shape(dtype, itype, avg_row, irregular, lanes_override, window_override);
         A->ntiles = nnz / A->shape.window + 1;
         if (A->ntiles >= (i64)INT32_MAX) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: too many tiles");
@@ -452,6 +580,13 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
             CU_TRY(cudaStreamSynchronize(st));
             cudaFree(d_cls);
         }
+    }
+    // Irregular matrices (most entries in tiles the row walk cannot take) multiply with the nnz-split kernel of flat.cu;
+    // the tile table above still serves the sparse x dense product.  HPCLA_SPMV_KIND=general keeps the tile kernel.
+    if (A->shape.lanes == 0 && kind != 2 && nnz > 0) {
+        CU_TRY(flat_build(itype, d_rowptr, nrows, nnz, &A->flat, st));
+        CU_TRY(cudaMalloc(&A->flat.d_heads, dtype_size(dtype) * (size_t)std::max<i64>(A->flat.n_wchunks, 1)));
+        if (const char* e = getenv("HPCLA_FLAT_KEEP_X")) A->flat_keep_x = e[0] == '1';
     }
     // rows longer than the split threshold (rare: power-law tails)
     const i64 cap = nnz / A->long_threshold + 1;
@@ -517,6 +652,7 @@ extern "C" void hpcla_csr_destroy(hpcla_csr* A) {
     cudaFree(A->d_long_rows);
     cudaFree(A->d_chunk_ptr);
     cudaFree(A->d_partials);
+    flat_free(&A->flat);
     delete A;
 }
 
@@ -527,6 +663,55 @@ static bool is_consecutive(const std::vector<i64>& v) {
     for (size_t k = 1; k < v.size(); ++k)
         if (v[k] != v[k - 1] + 1) return false;
     return true;
+}
+
+// Compact data for the interior row-walk tiles (compact.cu): analysis pass (x runs and staged x elements per tile), the
+// staged-x capacity from it, then headers + 16-bit positions for the tiles that fit.  HPCLA_COMPACT=0 disables.
+static int build_compact(hpcla_spmv* op, std::vector<int> (&lists)[3][2]) {
+    const hpcla_csr* A = op->csr;
+    const char* env = getenv("HPCLA_COMPACT");
+    if (env && env[0] == '0') return HPCLA_OK;
+    if (A->shape.lanes <= 0 || !op->x_in_place || op->own_n >= (i64)INT32_MAX || lists[0][0].empty()) return HPCLA_OK;
+    CompactShape sh = compact_shape(A->dtype, A->shape);
+    if (sh.cw <= 0 || sh.cw > 8192) return HPCLA_OK;
+    cudaStream_t st = op->ctx->halo_stream;
+    const int n = (int)lists[0][0].size();
+    int* d_ids = nullptr;
+    int2* d_stats = nullptr;
+    CU_TRY(cudaMalloc(&d_ids, sizeof(int) * (size_t)n));
+    CU_TRY(cudaMalloc(&d_stats, sizeof(int2) * (size_t)n));
+    struct Free2 {
+        int*& a;
+        int2*& b;
+        ~Free2() { cudaFree(a), cudaFree(b); }
+    } free2{d_ids, d_stats};
+    CU_TRY(cudaMemcpyAsync(d_ids, lists[0][0].data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
+    CU_TRY(launch_compact_tiles(false, A->dtype, A->itype, A->d_rowptr, A->d_colval, A->d_tiles, d_ids, n, A->shape.window, op->own_lo, op->own_n, sh, d_stats,
+                                nullptr, nullptr, st));
+    std::vector<int2> stats((size_t)n);
+    CU_TRY(cudaMemcpyAsync(stats.data(), d_stats, sizeof(int2) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    // staged x may take as many elements as the tile stages entries (the 7-point stencil needs ~0.72 of that, the 27-point ~0.34)
+    const int limit = sh.cw;
+    int xmax = 0, n_ok = 0;
+    for (const int2& s2 : stats)
+        if (s2.x >= 0 && s2.y <= limit) xmax = std::max(xmax, s2.y), ++n_ok;
+    if (n_ok * 2 < n || xmax == 0) return HPCLA_OK;  // not a banded matrix: the plain row walk keeps its tiles
+    sh.xcap = (xmax + 7) & ~7;
+    std::vector<int> chosen, rest;
+    for (int i = 0; i < n; ++i) (stats[(size_t)i].x >= 0 && stats[(size_t)i].y <= limit ? chosen : rest).push_back(lists[0][0][(size_t)i]);
+    const int nc = (int)chosen.size();
+    CU_TRY(cudaMemcpyAsync(d_ids, chosen.data(), sizeof(int) * (size_t)nc, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMalloc(&op->d_chdr, (size_t)nc * (size_t)sh.chdr_bytes));
+    CU_TRY(cudaMalloc(&op->d_cpos, (size_t)nc * (size_t)sh.cp_bytes));
+    CU_TRY(cudaMemsetAsync(op->d_chdr, 0, (size_t)nc * (size_t)sh.chdr_bytes, st));
+    CU_TRY(launch_compact_tiles(true, A->dtype, A->itype, A->d_rowptr, A->d_colval, A->d_tiles, d_ids, nc, A->shape.window, op->own_lo, op->own_n, sh, nullptr,
+                                op->d_chdr, op->d_cpos, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    op->csh = sh;
+    lists[2][0].swap(chosen);
+    lists[0][0].swap(rest);
+    return HPCLA_OK;
 }
 
 extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan* plan, int64_t n_x_local, hpcla_spmv** out) {
@@ -597,6 +782,10 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
     CU_TRY(cudaEventCreateWithFlags(&op->ev_x, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&op->ev_packed, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&op->ev_halo, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&op->ev_last, cudaEventDisableTiming));
+    if (const char* e = getenv("HPCLA_TIMELINE")) op->timeline = e[0] == '1';
+    if (op->timeline)
+        for (cudaEvent_t& e : op->tl) CU_TRY(cudaEventCreate(&e));
     // tile lists per kernel class, interior / boundary: a tile is boundary iff one of its stored columns is a ghost
     {
         std::vector<unsigned char> flags((size_t)A->ntiles, 0);
@@ -608,12 +797,14 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
             CU_TRY(cudaStreamSynchronize(ctx->halo_stream));
             cudaFree(d_flags);
         }
-        std::vector<int> (&lists)[2][2] = op->h_list;
+        std::vector<int> (&lists)[3][2] = op->h_list;
         for (i64 t = 0; t < A->ntiles; ++t) {
             const int c = A->tile_class[(size_t)t];
             if (c) lists[c - 1][flags[(size_t)t] ? 1 : 0].push_back((int)t);
         }
-        for (int c = 0; c < 2; ++c)
+        rc = build_compact(op, lists);  // moves the interior row-walk tiles that can be compacted to lists[2][0]
+        if (rc) return rc;
+        for (int c = 0; c < 3; ++c)
             for (int g = 0; g < 2; ++g) {
                 op->n_list[c][g] = (int)lists[c][g].size();
                 if (lists[c][g].empty()) continue;
@@ -641,10 +832,17 @@ extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan*
 
 extern "C" int hpcla_spmv_info(const hpcla_spmv* op, int64_t* n_int, int64_t* n_bnd, int* x_in_place, int* sends_contiguous) {
     if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_info: null");
-    if (n_int) *n_int = op->n_list[0][0] + op->n_list[1][0];
+    if (n_int) *n_int = op->n_list[0][0] + op->n_list[1][0] + op->n_list[2][0];
     if (n_bnd) *n_bnd = op->n_list[0][1] + op->n_list[1][1];
     if (x_in_place) *x_in_place = op->x_in_place ? 1 : 0;
     if (sends_contiguous) *sends_contiguous = op->sends_contiguous ? 1 : 0;
+    return HPCLA_OK;
+}
+extern "C" int hpcla_spmv_tile_lists(const hpcla_spmv* op, int64_t* out6) {
+    if (!op || !out6) return fail(HPCLA_ERR_ARG, "hpcla_spmv_tile_lists: null");
+    out6[0] = op->n_list[0][0], out6[1] = op->n_list[0][1], out6[2] = op->n_list[1][0], out6[3] = op->n_list[1][1];
+    out6[4] = op->n_list[2][0];
+    out6[5] = op->csr->flat.n_chunks;
     return HPCLA_OK;
 }
 extern "C" int64_t hpcla_spmv_launch_count(const hpcla_spmv* op) { return op ? op->launches : -1; }
@@ -652,7 +850,19 @@ extern "C" int64_t hpcla_spmv_launch_count(const hpcla_spmv* op) { return op ? o
 extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
     if (!op) return;
     cudaSetDevice(op->ctx->device);
-    cudaDeviceSynchronize();
+    // wait for this operator's own work (halo stream + the end of its last call on the caller's stream), not the device
+    cudaStreamSynchronize(op->ctx->halo_stream);
+    if (op->ev_last) cudaEventSynchronize(op->ev_last);
+    if (op->pipe) {
+        if (op->ctx->h2d_stream) cudaStreamSynchronize(op->ctx->h2d_stream);
+        if (op->ctx->d2h_stream) cudaStreamSynchronize(op->ctx->d2h_stream);
+    }
+    if (op->graph) cudaGraphExecDestroy(op->graph);
+    if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
+    cudaFree(op->d_cg_scalars);
+    for (cudaEvent_t e : op->tl)
+        if (e) cudaEventDestroy(e);
+    if (op->ev_last) cudaEventDestroy(op->ev_last);
     if (op->ctx->group) {
         hpcla_group* g = op->ctx->group;
         std::lock_guard<std::mutex> lk(g->mu);
@@ -665,8 +875,10 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
     cudaFree(op->d_send_idx);
     cudaFree(op->d_local_src);
     cudaFree(op->d_local_dst);
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 3; ++c)
         for (int g = 0; g < 2; ++g) cudaFree(op->d_list[c][g]);
+    cudaFree(op->d_chdr);
+    cudaFree(op->d_cpos);
     cudaFree(op->d_dot_partials);
     if (op->pipe) {
         for (cudaEvent_t e : op->pipe->ev_in) cudaEventDestroy(e);
@@ -742,12 +954,16 @@ static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream, 
         for (const Seg& s : op->sends) {
             // all runs contiguous in x.v (every stencil): send straight from x, no pack kernel, no copy
             const char* src = op->sends_contiguous ? (const char*)d_x + (size_t)(s.src0 - 1) * es : (const char*)op->d_sendbuf + (size_t)s.start * es;
-            NCCL_TRY(api->Send(src, (size_t)s.count * per, nt, s.peer, ctx->comm, hs));
+            NCCL_TRY_IN_GROUP(api->Send(src, (size_t)s.count * per, nt, s.peer, ctx->comm, hs));
         }
-        for (const Seg& r : op->recvs) NCCL_TRY(api->Recv((char*)op->d_gathered + (size_t)(r.start - 1) * es, (size_t)r.count * per, nt, r.peer, ctx->comm, hs));
+        for (const Seg& r : op->recvs) NCCL_TRY_IN_GROUP(api->Recv((char*)op->d_gathered + (size_t)(r.start - 1) * es, (size_t)r.count * per, nt, r.peer, ctx->comm, hs));
         NCCL_TRY(api->GroupEnd());
         CU_TRY(cudaEventRecord(op->ev_halo, hs));
         op->halo_recorded = true;
+        if (op->timeline) {
+        CU_TRY(cudaEventRecord(op->tl[1], hs));
+        op->tl_rec[1] = true;
+    }
     }
     return HPCLA_OK;
 }
@@ -822,22 +1038,65 @@ static bool tile_runs(const std::vector<std::pair<int, int>>& runs, int lo, int 
 // both kernel classes over the interior (which = 0) or boundary (which = 1) tiles
 // (from, to: positions in the lists, per class; nullptr = the whole lists)
 static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t stream, const int* from = nullptr, const int* to = nullptr) {
-    for (int c = 0; c < 2; ++c) {
+    for (int c = 0; c < 3; ++c) {
         const int lo = from ? from[c] : 0, hi = to ? to[c] : op->n_list[c][which];
         L.recs = op->d_list[c][which] + lo;
         L.n_launch = hi - lo;
         if (L.n_launch <= 0) continue;
         const bool runs = tile_runs(op->runs[c][which], lo, hi, L);
         L.dot_x = nullptr;
-        if (c == 0 && op->dot_request) {  // whole lists only (hpcla_cg): partials of the interior list, then the boundary list
+        if (c != 1 && op->dot_request) {  // whole lists only (hpcla_cg): partials of the interior lists (class 0, then 2), then the boundary list
             L.dot_x = op->cur_x;
-            L.dot_out = op->d_dot_partials + (which == 1 ? op->n_list[0][0] : 0);
+            L.dot_out = op->d_dot_partials + (which == 1 ? op->n_list[0][0] + op->n_list[2][0] : c == 2 ? op->n_list[0][0] : 0);
         }
-        if (c == 0 && runs && !L.has_ghost && op->csr->d_hdrs && !op->dot_request) CU_TRY(launch_spmv_direct(L, stream));
-        else if (c == 0) CU_TRY(launch_spmv_rowwalk(L, stream));
+        if (c == 2 && runs && (((uintptr_t)L.x_own) & 15) == 0) {  // compact tiles: x runs are fetched with 16-byte bulk copies
+            CWalkLaunch C;
+            C.dtype = L.dtype;
+            C.lanes = L.shape.lanes;
+            C.window = L.shape.window;
+            C.nzval = L.nzval;
+            C.nnz = L.nnz;
+            C.sh = op->csh;
+            C.hdrs = op->d_chdr;
+            C.colpos = op->d_cpos;
+            C.q0 = lo;
+            C.n_runs = L.n_runs;
+            for (int j = 0; j < 9; ++j) C.run_cta0[j] = L.run_cta0[j];
+            for (int j = 0; j < 8; ++j) C.run_tile0[j] = L.run_tile0[j];
+            C.n_launch = L.n_launch;
+            C.x_own = L.x_own;
+            C.y = L.y;
+            C.dot_x = L.dot_x;
+            C.dot_out = L.dot_out;
+            CU_TRY(launch_spmv_cwalk(C, stream));
+        } else if (c != 1 && runs && !L.has_ghost && op->csr->d_hdrs && !op->dot_request) CU_TRY(launch_spmv_direct(L, stream));
+        else if (c != 1) CU_TRY(launch_spmv_rowwalk(L, stream));
         else CU_TRY(launch_spmv_general(L, stream));
         op->launches += 1;
     }
+    return HPCLA_OK;
+}
+
+// irregular matrices: the nnz-split multiply over all stored entries, then the fix-up of rows that span warp chunks
+static int launch_flat(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stream) {
+    const hpcla_csr* A = op->csr;
+    FlatLaunch F;
+    F.dtype = A->dtype;
+    F.itype = A->itype;
+    F.colval = A->d_colval;
+    F.nzval = A->d_nzval;
+    F.nnz = A->nnz;
+    F.flat = &A->flat;
+    F.x_own = base.x_own;
+    F.gathered = base.gathered;
+    F.own_lo = base.own_lo;
+    F.own_n = base.own_n;
+    F.has_ghost = base.has_ghost;
+    F.keep_x = A->flat_keep_x;
+    F.y = base.y;
+    F.long_threshold = A->long_threshold;
+    CU_TRY(launch_spmv_flat(F, stream));
+    op->launches += 2 + (A->flat.n_empty > 0 ? 1 : 0);
     return HPCLA_OK;
 }
 
@@ -876,6 +1135,11 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     op->cur_x = d_x;
     op->cur_y = d_y;
     op->cur_stream = stream;
+    if (op->timeline) {
+        for (bool& b : op->tl_rec) b = false;
+        CU_TRY(cudaEventRecord(op->tl[0], stream));
+        op->tl_rec[0] = true;
+    }
     if (op->has_peers) {
         rc = exchange_begin(op, d_x, stream);
         if (rc) return rc;
@@ -887,11 +1151,32 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
     }
     SpmvLaunch L;
     fill_launch(op, L, d_x, d_y);
+    if (op->csr->flat.n_chunks > 0) {
+        // irregular matrix: every chunk of the nonzero stream may read ghosts (random columns), so with ghosts the whole
+        // multiply runs behind the halo (hpcla_spmv_finish); without, here
+        if (!op->has_ghost) {
+            L.has_ghost = false;
+            rc = launch_flat(op, L, stream);
+            if (rc) return rc;
+            rc = launch_long(op, L, stream);
+            if (rc) return rc;
+        }
+        if (op->timeline) {
+        CU_TRY(cudaEventRecord(op->tl[3], stream));
+        op->tl_rec[3] = true;
+    }
+        op->phase = 1;
+        return HPCLA_OK;
+    }
     // interior tiles (all tiles when there are no ghosts) read own columns only: the ghost-free kernels, run while the
     // halo is in flight
     L.has_ghost = false;
     rc = launch_tiles(op, L, 0, stream);
     if (rc) return rc;
+    if (op->timeline) {
+        CU_TRY(cudaEventRecord(op->tl[3], stream));
+        op->tl_rec[3] = true;
+    }
     if (!op->has_ghost) {
         rc = launch_long(op, L, stream);
         if (rc) return rc;
@@ -911,7 +1196,8 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
         rc = exchange_finish_group(op);
         if (rc) return rc;
     }
-    if (op->has_ghost) {
+    const bool flat = op->csr->flat.n_chunks > 0;
+    if (op->has_ghost && !flat) {
         // Boundary tiles go on the (high-priority) halo stream, right behind the receives: they run next to the
         // interior tiles instead of after them, so a step costs max(interior, halo + boundary), not their sum.
         SpmvLaunch L;
@@ -921,6 +1207,10 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
         if (rc) return rc;
         CU_TRY(cudaEventRecord(op->ev_halo, hs));
         op->halo_recorded = true;
+        if (op->timeline) {
+        CU_TRY(cudaEventRecord(op->tl[2], hs));
+        op->tl_rec[2] = true;
+    }
     }
     if (op->has_peers || op->has_ghost) {
         // x (contiguous sends) and the packed buffer are read on the halo stream: the caller's stream must not run
@@ -931,10 +1221,89 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
     if (op->has_ghost) {
         SpmvLaunch L;
         fill_launch(op, L, op->cur_x, op->cur_y);
+        if (flat) {
+            if (!op->x_in_place) CU_TRY(cudaStreamWaitEvent(stream, op->ev_x, 0));
+            rc = launch_flat(op, L, stream);
+            if (rc) return rc;
+        }
         rc = launch_long(op, L, stream);
         if (rc) return rc;
     }
+    if (op->timeline) {
+        CU_TRY(cudaEventRecord(op->tl[4], stream));
+        op->tl_rec[4] = true;
+    }
+    CU_TRY(cudaEventRecord(op->ev_last, stream));
     op->phase = 0;
+    return HPCLA_OK;
+}
+
+// Timeline of the most recent multiply (HPCLA_TIMELINE=1 when the operator was created): milliseconds from the moment
+// x was ready on the caller's stream to [0] the end of the halo exchange (halo stream), [1] the end of the boundary
+// tiles (halo stream), [2] the end of the interior tiles (caller's stream), [3] the end of the call (caller's stream);
+// -1 where the step does not exist (no peers / no ghosts).  Blocks until the multiply has finished.
+extern "C" int hpcla_spmv_timeline(hpcla_spmv* op, double* ms4_out) {
+    if (!op || !ms4_out) return fail(HPCLA_ERR_ARG, "hpcla_spmv_timeline: null");
+    if (!op->timeline) return fail(HPCLA_ERR_STATE, "hpcla_spmv_timeline: the operator was created without HPCLA_TIMELINE=1");
+    if (!op->tl_rec[0] || !op->tl_rec[4]) return fail(HPCLA_ERR_STATE, "hpcla_spmv_timeline: no multiply has run yet");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    CU_TRY(cudaEventSynchronize(op->tl[4]));
+    CU_TRY(cudaStreamSynchronize(op->ctx->halo_stream));
+    for (int k = 1; k <= 4; ++k) {
+        float ms = -1.f;
+        if (op->tl_rec[k]) CU_TRY(cudaEventElapsedTime(&ms, op->tl[0], op->tl[k]));
+        ms4_out[k - 1] = (double)ms;
+    }
+    return HPCLA_OK;
+}
+
+// One multiply as a CUDA graph bound to fixed x.v / y.v: the event choreography between the caller's stream and the
+// halo stream becomes graph dependencies, the grouped ncclSend/ncclRecv a captured kernel node, and a replay costs one
+// launch instead of ~10 driver calls — what the latency-bound strong-scaling regime needs.
+// NCCL world or a single rank.  capture: (re)builds the graph; launch: replays it on `stream`.
+extern "C" int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d_y, void* stream_) {
+    if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_graph_capture: null");
+    if (op->ctx->group && op->ctx->nranks > 1 && op->has_peers) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: needs an NCCL world or a single rank");
+    if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: the previous call was not finished");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (op->graph) {
+        cudaGraphExecDestroy(op->graph);
+        op->graph = nullptr;
+    }
+    const bool tl = op->timeline;
+    op->timeline = false;  // timing events are not captured
+    const i64 before = op->launches;
+    cudaGraph_t g = nullptr;
+    CU_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+    rc = hpcla_spmv_run(op, d_x, d_y, stream);
+    cudaError_t ce = cudaStreamEndCapture(stream, &g);
+    op->timeline = tl;
+    op->phase = 0;
+    if (rc || ce != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return rc ? rc : fail(HPCLA_ERR_CUDA, "hpcla_spmv_graph_capture: cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    }
+    op->graph_launches = op->launches - before;
+    op->launches = before;
+    ce = cudaGraphInstantiate(&op->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) return fail(HPCLA_ERR_CUDA, "hpcla_spmv_graph_capture: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+    op->graph_x = d_x;
+    op->graph_y = d_y;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_graph_launch(hpcla_spmv* op, void* stream_) {
+    if (!op || !op->graph) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_launch: no captured graph");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    CU_TRY(cudaGraphLaunch(op->graph, (cudaStream_t)stream_));
+    CU_TRY(cudaEventRecord(op->ev_last, (cudaStream_t)stream_));
+    op->launches += op->graph_launches;
     return HPCLA_OK;
 }
 
@@ -981,12 +1350,12 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
         L.k0 = k0;
         const int left = op->mm_ncols - k0;
         L.kn = (left >= 8 && spmm_k8) ? 8 : left >= 4 ? 4 : 1;
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < 3; ++c) {
             L.recs = op->d_list[c][which];
             L.n_launch = op->n_list[c][which];
             if (L.n_launch <= 0) continue;
             tile_runs(op->runs[c][which], 0, L.n_launch, L);
-            if (c == 0 && walk) CU_TRY(launch_spmm_rowwalk(L, stream));
+            if (c != 1 && walk) CU_TRY(launch_spmm_rowwalk(L, stream));
             else CU_TRY(launch_spmm_rows(L, stream));
             op->launches += 1;
         }
@@ -1012,8 +1381,10 @@ extern "C" int hpcla_spmm_begin(hpcla_spmv* op, const void* d_B, int64_t ldb, vo
     op->mm_ldc = ldc;
     op->mm_ncols = ncols;
     op->cur_stream = stream;
-    op->phase = 3;
-    if (ncols == 0) return HPCLA_OK;
+    if (ncols == 0) {
+        op->phase = 3;
+        return HPCLA_OK;
+    }
     const i64 n_ghost = op->plan.n_gathered - op->own_n;
     if (op->has_peers && ncols > op->mm_cols) {  // (re)size the exchange buffers
         CU_TRY(cudaDeviceSynchronize());
@@ -1045,13 +1416,16 @@ extern "C" int hpcla_spmm_begin(hpcla_spmv* op, const void* d_B, int64_t ldb, vo
             const ncclDataType_t nt = nccl_type(dtype, &per);
             NCCL_TRY(api->GroupStart());
             for (const Seg& sg : op->sends)  // one message per peer: its rows, all columns adjacent
-                NCCL_TRY(api->Send((const char*)op->d_sendbuf_rm + (size_t)sg.start * ncols * es, (size_t)sg.count * ncols * per, nt, sg.peer, ctx->comm, hs));
+                NCCL_TRY_IN_GROUP(api->Send((const char*)op->d_sendbuf_rm + (size_t)sg.start * ncols * es, (size_t)sg.count * ncols * per, nt, sg.peer, ctx->comm, hs));
             for (const Seg& r : op->recvs)
-                NCCL_TRY(api->Recv((char*)op->d_ghost_rm + (size_t)ghost_number(op, r.start) * ncols * es, (size_t)r.count * ncols * per, nt, r.peer, ctx->comm, hs));
+                NCCL_TRY_IN_GROUP(api->Recv((char*)op->d_ghost_rm + (size_t)ghost_number(op, r.start) * ncols * es, (size_t)r.count * ncols * per, nt, r.peer, ctx->comm, hs));
             NCCL_TRY(api->GroupEnd());
         }
     }
-    return spmm_tiles(op, 0, false, stream);  // interior tiles while the halo is in flight
+    rc = spmm_tiles(op, 0, false, stream);  // interior tiles while the halo is in flight
+    if (rc) return rc;
+    op->phase = 3;  // only now: a failure above leaves the operator idle, not wedged
+    return HPCLA_OK;
 }
 
 extern "C" int hpcla_spmm_finish(hpcla_spmv* op) {
@@ -1118,7 +1492,7 @@ static int build_pipe(hpcla_spmv* op) {
     int nb = (int)std::min<i64>(64, std::max<i64>(1, (bytes + chunk_bytes - 1) / chunk_bytes));
     if ((i64)nb > A->ntiles) nb = (int)std::max<i64>(1, A->ntiles);
     // pipelining needs x.v read in place (own columns straight from x.v) and something to overlap
-    P->usable = op->x_in_place && nb >= 2 && A->nrows > 0 && op->n_x_local > 0;
+    P->usable = op->x_in_place && nb >= 2 && A->nrows > 0 && op->n_x_local > 0 && A->flat.n_chunks == 0;  // (a flat multiply needs all of x)
     if (!P->usable) return HPCLA_OK;
     P->nb = nb;
     // block boundaries in tiles, rows, and list positions
@@ -1129,7 +1503,7 @@ static int build_pipe(hpcla_spmv* op) {
         tb[(size_t)k] = (i64)k * A->ntiles / nb;
         P->row_at[(size_t)k] = k == nb ? A->nrows : tiles[(size_t)tb[(size_t)k]].row;
     }
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 3; ++c)
         for (int g = 0; g < 2; ++g) {
             const std::vector<int>& l = op->h_list[c][g];
             P->pos[c][g].resize((size_t)nb + 1);
@@ -1152,7 +1526,7 @@ static int build_pipe(hpcla_spmv* op) {
     int running = -1;
     for (int k = 0; k < nb; ++k) {
         i64 need = -1;
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 3; ++c)
             for (int q = P->pos[c][0][(size_t)k]; q < P->pos[c][0][(size_t)k + 1]; ++q) need = std::max(need, maxcol[(size_t)op->h_list[c][0][(size_t)q]]);
         if (need >= 0) {
             const i64 xi = need + op->own_src0 - 1;  // 0-based index into x.v
@@ -1161,7 +1535,7 @@ static int build_pipe(hpcla_spmv* op) {
             running = std::max(running, j);
         }
         P->in_chunk[(size_t)k] = running;
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 3; ++c)
             if (P->pos[c][1][(size_t)k + 1] > P->pos[c][1][(size_t)k]) P->late[(size_t)k] = 1;
     }
     if (A->nlong > 0) {
@@ -1230,7 +1604,8 @@ extern "C" int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x,
             waited = P->in_chunk[(size_t)k];
             CU_TRY(cudaStreamWaitEvent(stream, P->ev_in[(size_t)waited], 0));
         }
-        const int from[2] = {P->pos[0][0][(size_t)k], P->pos[1][0][(size_t)k]}, to[2] = {P->pos[0][0][(size_t)k + 1], P->pos[1][0][(size_t)k + 1]};
+        const int from[3] = {P->pos[0][0][(size_t)k], P->pos[1][0][(size_t)k], P->pos[2][0][(size_t)k]};
+        const int to[3] = {P->pos[0][0][(size_t)k + 1], P->pos[1][0][(size_t)k + 1], P->pos[2][0][(size_t)k + 1]};
         rc = launch_tiles(op, L, 0, stream, from, to);
         if (rc) return rc;
         if (!P->late[(size_t)k]) {
@@ -1381,10 +1756,37 @@ extern "C" int hpcla_repartition_run(hpcla_ctx* ctx, int dtype, int64_t n_send, 
         const ncclDataType_t nt = nccl_type(dtype, &per);
         NCCL_TRY(api->GroupStart());
         for (i64 i = 0; i < n_send; ++i)
-            NCCL_TRY(api->Send((const char*)d_src + (size_t)(send_first[i] - 1) * es, (size_t)send_count[i] * per, nt, (int)send_rank_ids[i], ctx->comm, stream));
+            NCCL_TRY_IN_GROUP(api->Send((const char*)d_src + (size_t)(send_first[i] - 1) * es, (size_t)send_count[i] * per, nt, (int)send_rank_ids[i], ctx->comm, stream));
         for (i64 i = 0; i < n_recv; ++i)
-            NCCL_TRY(api->Recv((char*)d_dst + (size_t)(recv_offset[i] - 1) * es, (size_t)recv_count[i] * per, nt, (int)recv_rank_ids[i], ctx->comm, stream));
+            NCCL_TRY_IN_GROUP(api->Recv((char*)d_dst + (size_t)(recv_offset[i] - 1) * es, (size_t)recv_count[i] * per, nt, (int)recv_rank_ids[i], ctx->comm, stream));
         NCCL_TRY(api->GroupEnd());
+    }
+    return HPCLA_OK;
+}
+
+// The device side of hpcla_cg: everything is enqueued, nothing is read back (capturable into a CUDA graph).
+static int cg_enqueue(hpcla_spmv* op, const void* d_b, void* d_x, char* r, char* p, char* q, int iters, bool fused, i64 n_partials, double* d_s,
+                      double* d_pq, cudaStream_t stream) {
+    hpcla_ctx* ctx = op->ctx;
+    const int dtype = op->csr->dtype;
+    const i64 n = op->csr->nrows;
+    const bool multi = ctx->comm && ctx->nranks > 1;
+    NcclApi* api = multi ? nccl_api() : nullptr;
+    CU_TRY(launch_cg_init(dtype, n, d_b, d_x, r, p, ctx->d_red_scratch, d_s, stream));
+    op->launches += 1;
+    if (multi) NCCL_TRY(api->AllReduce(d_s, d_s, 1, ncclFloat64, ncclSum, ctx->comm, stream));
+    for (int k = 0; k < iters; ++k) {
+        op->dot_request = fused;
+        int rc = hpcla_spmv_run(op, p, q, stream);
+        op->dot_request = false;
+        if (rc) return rc;
+        if (fused) CU_TRY(launch_dot_partials_sum(op->d_dot_partials, n_partials, d_pq, stream));
+        else CU_TRY(launch_dot(dtype, n, p, q, ctx->d_red_scratch, d_pq, stream));
+        if (multi) NCCL_TRY(api->AllReduce(d_pq, d_pq, 1, ncclFloat64, ncclSum, ctx->comm, stream));
+        CU_TRY(launch_cg_update_xr(dtype, n, p, q, d_x, r, d_s + 2 * k, d_pq, ctx->d_red_scratch, d_s + 2 * (k + 1), stream));
+        if (multi) NCCL_TRY(api->AllReduce(d_s + 2 * (k + 1), d_s + 2 * (k + 1), 1, ncclFloat64, ncclSum, ctx->comm, stream));
+        CU_TRY(launch_cg_update_p(dtype, n, r, p, d_s + 2 * (k + 1), d_s + 2 * k, stream));
+        op->launches += 3;
     }
     return HPCLA_OK;
 }
@@ -1404,38 +1806,63 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     char* r = (char*)d_work;
     char* p = r + (size_t)n * es;
     char* q = p + (size_t)n * es;
-    double* d_s = nullptr;  // rr_k at [2k], pq at the tail
-    CU_TRY(cudaMalloc(&d_s, sizeof(double) * (size_t)(2 * (iters + 1) + 2)));
-    struct FreeOnExit {
-        double* p;
-        ~FreeOnExit() { cudaFree(p); }
-    } free_d_s{d_s};
-    double* d_pq = d_s + 2 * (iters + 1);
-    const bool multi = ctx->comm && ctx->nranks > 1;
-    NcclApi* api = multi ? nccl_api() : nullptr;
-    CU_TRY(launch_cg_init(dtype, n, d_b, d_x, r, p, ctx->d_red_scratch, d_s, stream));
-    op->launches += 1;
-    if (multi) NCCL_TRY(api->AllReduce(d_s, d_s, 1, ncclFloat64, ncclSum, ctx->comm, stream));
+    if (op->cg_cap < iters) {  // rr_k at [2k], pq at the tail; kept by the operator, grown on demand
+        CU_TRY(cudaStreamSynchronize(stream));
+        cudaFree(op->d_cg_scalars);
+        op->d_cg_scalars = nullptr;
+        op->cg_cap = 0;
+        const int cap = std::max(iters, 64);
+        CU_TRY(cudaMalloc(&op->d_cg_scalars, sizeof(double) * (size_t)(2 * (cap + 1) + 2)));
+        op->cg_cap = cap;
+    }
+    double* d_s = op->d_cg_scalars;
+    double* d_pq = d_s + 2 * (op->cg_cap + 1);
     // p.q rides on the multiply when every row goes through the row-walk kernel (stencil-like matrices): the multiply
     // leaves one partial per CTA, a one-CTA kernel adds them in a fixed order — p and q are not read a second time
-    const i64 n_partials = (i64)op->n_list[0][0] + op->n_list[0][1];
-    const bool fused = op->n_list[1][0] + op->n_list[1][1] == 0 && op->csr->nlong == 0 && op->x_in_place && op->own_src0 == 1 && n_partials > 0 &&
-                       !getenv("HPCLA_CG_UNFUSED");
+    const i64 n_partials = (i64)op->n_list[0][0] + op->n_list[2][0] + op->n_list[0][1];
+    const bool fused = op->n_list[1][0] + op->n_list[1][1] == 0 && op->csr->nlong == 0 && op->csr->flat.n_chunks == 0 && op->x_in_place &&
+                       op->own_src0 == 1 && n_partials > 0 && !getenv("HPCLA_CG_UNFUSED");
     if (fused && !op->d_dot_partials) CU_TRY(cudaMalloc(&op->d_dot_partials, sizeof(double) * (size_t)n_partials));
-    for (int k = 0; k < iters; ++k) {
-        op->dot_request = fused;
-        rc = hpcla_spmv_run(op, p, q, stream);
-        op->dot_request = false;
-        if (rc) return rc;
-        if (fused) CU_TRY(launch_dot_partials_sum(op->d_dot_partials, n_partials, d_pq, stream));
-        else CU_TRY(launch_dot(dtype, n, p, q, ctx->d_red_scratch, d_pq, stream));
-        if (multi) NCCL_TRY(api->AllReduce(d_pq, d_pq, 1, ncclFloat64, ncclSum, ctx->comm, stream));
-        CU_TRY(launch_cg_update_xr(dtype, n, p, q, d_x, r, d_s + 2 * k, d_pq, ctx->d_red_scratch, d_s + 2 * (k + 1), stream));
-        if (multi) NCCL_TRY(api->AllReduce(d_s + 2 * (k + 1), d_s + 2 * (k + 1), 1, ncclFloat64, ncclSum, ctx->comm, stream));
-        CU_TRY(launch_cg_update_p(dtype, n, r, p, d_s + 2 * (k + 1), d_s + 2 * k, stream));
-        op->launches += 3;
+    // HPCLA_CG_GRAPH=1: the whole loop (iters x {multiply + halo, p.q, Allreduce, x/r update, Allreduce, p update}) as ONE
+    // CUDA graph, re-used while the buffers and the iteration count stay the same: one launch instead of ~12 * iters
+    // driver calls (the regime where the host, not the device, paces the loop).
+    static const bool want_graph = [] { const char* e = getenv("HPCLA_CG_GRAPH"); return e && e[0] == '1'; }();
+    const bool same = op->cg_graph && op->cg_key_b == d_b && op->cg_key_x == d_x && op->cg_key_w == d_work && op->cg_key_iters == iters && op->cg_key_fused == fused;
+    if (want_graph && same) {
+        CU_TRY(cudaGraphLaunch(op->cg_graph, stream));
+        op->launches += op->cg_graph_launches;
+    } else {
+        const i64 before = op->launches;
+        if (want_graph) {
+            if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
+            op->cg_graph = nullptr;
+            CU_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+        }
+        const bool tl = op->timeline;
+        if (want_graph) op->timeline = false;
+        rc = cg_enqueue(op, d_b, d_x, r, p, q, iters, fused, n_partials, d_s, d_pq, stream);
+        op->timeline = tl;
+        if (want_graph) {
+            cudaGraph_t g = nullptr;
+            cudaError_t ce = cudaStreamEndCapture(stream, &g);
+            op->phase = 0;
+            if (rc || ce != cudaSuccess || !g) {
+                if (g) cudaGraphDestroy(g);
+                cudaGetLastError();
+                return rc ? rc : fail(HPCLA_ERR_CUDA, "hpcla_cg: graph capture failed: %s", cudaGetErrorString(ce));
+            }
+            ce = cudaGraphInstantiate(&op->cg_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (ce != cudaSuccess) return fail(HPCLA_ERR_CUDA, "hpcla_cg: cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+            op->cg_key_b = d_b, op->cg_key_x = d_x, op->cg_key_w = d_work, op->cg_key_iters = iters, op->cg_key_fused = fused;
+            op->cg_graph_launches = op->launches - before;
+            CU_TRY(cudaGraphLaunch(op->cg_graph, stream));
+        } else if (rc) {
+            return rc;
+        }
     }
-    std::vector<double> h((size_t)(2 * (iters + 1)));
+    std::vector<double>& h = op->cg_host;
+    h.resize((size_t)(2 * (iters + 1)));
     CU_TRY(cudaMemcpyAsync(h.data(), d_s, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, stream));
     CU_TRY(cudaStreamSynchronize(stream));
     if (rr_history_out)

@@ -115,6 +115,71 @@ cudaError_t launch_spmm_rows(const SpmmLaunch& L, cudaStream_t st);     // any t
 // out[i * ncols + k] = B[idx[i] - 1 + k * ldb]
 cudaError_t launch_pack_rows(int dtype, const void* B, i64 ldb, const i64* idx, i64 n, int ncols, void* out, cudaStream_t st);
 
+// Row walk on compact tiles (compact.cu): per (matrix, plan) derived data of the interior row-walk tiles
+struct CompactShape {
+    int crows;       // rows a compact tile header can describe
+    int chdr_bytes;  // bytes per tile header (multiple of 16)
+    int chdr_fetch;  // bytes of it the multiply fetches
+    int cw;          // staged entries per tile (window + over-fetch, multiple of 8)
+    int cp_bytes;    // bytes of 16-bit positions per tile
+    int xcap;        // staged x elements per tile
+};
+CompactShape compact_shape(int dtype, const TileShape& shape);
+size_t cwalk_smem_bytes(int dtype, const CompactShape& sh);
+// one CTA per listed tile: build == false: stats[i] = {x runs or -1, staged x elements}; build == true: headers + positions
+cudaError_t launch_compact_tiles(bool build, int dtype, int itype, const void* rowptr, const void* colval, const TileDesc* tiles, const int* d_tile_ids, int n,
+                                 int window, i64 own_lo, i64 own_n, const CompactShape& sh, int2* d_stats, unsigned char* d_hdrs, unsigned char* d_colpos,
+                                 cudaStream_t st);
+struct CWalkLaunch {
+    int dtype, lanes, window;
+    const void* nzval;
+    i64 nnz;
+    CompactShape sh;
+    const unsigned char* hdrs;
+    const unsigned char* colpos;
+    int q0;  // position of the first CTA's tile in the compact list
+    int n_runs = 0;
+    int run_cta0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int run_tile0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n_launch;
+    const void* x_own;  // first own element of x.v; 16-byte aligned
+    void* y;
+    const void* dot_x = nullptr;
+    double* dot_out = nullptr;
+};
+cudaError_t launch_spmv_cwalk(const CWalkLaunch& L, cudaStream_t st);
+
+// nnz-split multiply for irregular matrices (flat.cu): per-matrix derived structure
+struct FlatData {
+    i64 n_chunks = 0;     // CTA chunks of 4096 stored entries (0: the matrix does not use the flat kernel)
+    i64 n_wchunks = 0;    // warp chunks of 512 stored entries that hold entries
+    i64 n_nonempty = 0, n_empty = 0;
+    unsigned* d_bits = nullptr;   // row-start flags, one bit per stored entry (padded to whole chunks)
+    i64* d_wrow = nullptr;        // per warp chunk: ordinal of the row holding its first entry
+    i64* d_row_map = nullptr;     // ordinal -> row (only when some rows are empty)
+    i64* d_empty_rows = nullptr;  // rows without entries (their y is zeroed)
+    void* d_heads = nullptr;      // T[n_wchunks]: partial sums in front of each warp chunk's first row start
+};
+struct FlatLaunch {
+    int dtype, itype;
+    const void* colval;
+    const void* nzval;
+    i64 nnz;
+    const FlatData* flat;
+    const void* x_own;
+    const void* gathered;
+    i64 own_lo, own_n;
+    bool has_ghost;
+    bool keep_x;  // gather x with an L2 evict-last hint
+    void* y;
+    i64 long_threshold;
+};
+cudaError_t flat_build(int itype, const void* rowptr, i64 nrows, i64 nnz, FlatData* out, cudaStream_t st);
+void flat_free(FlatData* F);
+cudaError_t launch_spmv_flat(const FlatLaunch& L, cudaStream_t st);
+// counts violations of: rowptr[0] == 1, rowptr non-decreasing, rowptr[nrows] == nnz + 1, 1 <= colval <= ncc
+cudaError_t launch_validate_csr(int itype, const void* rowptr, const void* colval, i64 nrows, i64 nnz, i64 ncc, unsigned* d_bad, cudaStream_t st);
+
 struct LongRowsLaunch {
     int dtype, itype;
     const void* rowptr;

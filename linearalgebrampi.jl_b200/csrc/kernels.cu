@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(THREADS, HPCLA_GENERAL_MIN_CTAS) spmv_tile_ker
         const Ti* __restrict__ cb = a.colval + s4;
         const T* __restrict__ vb = a.nzval + s4;
         const i64 avail = a.nnz_total - s4;  // elements that exist from s4 on
+        const int head = (int)(s - s4);      // entries of the previous tile in front of this tile's first one
         for (int base = 0; base < (int)n; base += CHUNK) {
             Ti c[GROUPS][4];
             T v[GROUPS][4];
@@ -71,10 +72,16 @@ __global__ void __launch_bounds__(THREADS, HPCLA_GENERAL_MIN_CTAS) spmv_tile_ker
                 if (i + 4 <= avail && i < n) {
                     ld4_stream(cb + i, c[g]);
                     ld4_stream(vb + i, v[g]);
+                    // the 4-aligned hull [s4, ..) may hold up to 3 entries of the neighbouring tiles on either side: their
+                    // columns were not classified with this tile (an interior tile could read a neighbour's ghost column
+                    // through the ghost-free view), so they are replaced by a column that is always valid
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (i + k < head || i + k >= (int)n) c[g][k] = (Ti)a.safe_col;
                 } else {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const bool ok = (i + k < avail) && (i + k < n);
+                        const bool ok = (i + k < avail) && (i + k < n) && (i + k >= head);
                         c[g][k] = ok ? ld_stream(cb + i + k) : (Ti)a.safe_col;
                         v[g][k] = ok ? ld_stream(vb + i + k) : el_zero(T());
                     }
@@ -390,6 +397,18 @@ __global__ void __launch_bounds__(256) row_len_hist_kernel(const Ti* __restrict_
         if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
 }
 
+// one-time check of a borrowed CSR view (hpcla_csr_create): a bad row pointer or column would otherwise index shared
+// memory with a negative length or read x out of bounds on the device
+template <class Ti>
+__global__ void validate_csr_kernel(const Ti* __restrict__ rowptr, const Ti* __restrict__ colval, i64 nrows, i64 nnz, i64 ncc, unsigned* bad) {
+    const i64 stride = (i64)gridDim.x * blockDim.x, t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned mine = 0;
+    if (t == 0) mine += ((i64)rowptr[0] != 1) + ((i64)rowptr[nrows] != nnz + 1);
+    for (i64 r = t; r < nrows; r += stride) mine += (i64)rowptr[r] > (i64)rowptr[r + 1];
+    for (i64 k = t; k < nnz; k += stride) mine += (unsigned long long)((i64)colval[k] - 1) >= (unsigned long long)ncc;
+    if (mine) atomicAdd(bad, mine);
+}
+
 template <class Ti>
 __global__ void find_long_rows_kernel(const Ti* __restrict__ rowptr, i64 nrows, i64 threshold, i64* rows_out, i64 cap,
                                       unsigned long long* count) {
@@ -686,6 +705,13 @@ cudaError_t launch_row_len_hist(int itype, const void* rowptr, i64 nrows, unsign
     const int blocks = (int)std::min<i64>(148 * 8, (nrows + 255) / 256);
     if (itype == HPCLA_I32) row_len_hist_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, nrows, hist);
     else row_len_hist_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, nrows, hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_validate_csr(int itype, const void* rowptr, const void* colval, i64 nrows, i64 nnz, i64 ncc, unsigned* d_bad, cudaStream_t st) {
+    const int blocks = (int)std::min<i64>(148 * 8, (std::max(nrows, nnz) + 255) / 256 + 1);
+    if (itype == HPCLA_I32) validate_csr_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, (const int*)colval, nrows, nnz, ncc, d_bad);
+    else validate_csr_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, (const long long*)colval, nrows, nnz, ncc, d_bad);
     return cudaGetLastError();
 }
 

@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes
 import os
 import itertools
+import weakref
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -42,6 +43,8 @@ from .vectors import HPCVector, _current_stream, _digest, _to_device, _torch_dty
 _vector_plan_cache: Dict[tuple, "VectorPlan"] = {}
 # counts plan constructions (test hook for the memoisation behaviour)
 plan_build_count = 0
+# matrices that may hold bound operators: clear_plan_cache() drops those operators with the plans they were bound to
+_live_matrices: "weakref.WeakSet[HPCSparseMatrix]" = weakref.WeakSet()
 
 
 class _DevView:
@@ -78,6 +81,8 @@ class HPCSparseMatrix:
         # backend-derived device state lives beside the reference's fields (SURVEY §8b "side cache")
         self._csr: Optional[int] = None
         self._ops: Dict[tuple, int] = {}
+        self._graphs: Dict[tuple, tuple] = {}
+        _live_matrices.add(self)
 
     # -- constructors ------------------------------------------------------------------------------------------
     @staticmethod
@@ -189,11 +194,17 @@ class HPCSparseMatrix:
         return f"HPCSparseMatrix({m}x{n}, local rows={self.nrows_local}, nnz_local={self.nnz_local}, T={self.backend.T}, Ti={self.backend.Ti}, {self.backend.device})"
 
 
-def _drop_device_state(A: HPCSparseMatrix) -> None:
+def _drop_bound_ops(A: HPCSparseMatrix) -> None:
     L = _lib.lib()
     for op in A._ops.values():
         L.hpcla_spmv_destroy(op)
     A._ops.clear()
+    A._graphs.clear()
+
+
+def _drop_device_state(A: HPCSparseMatrix) -> None:
+    L = _lib.lib()
+    _drop_bound_ops(A)
     if A._csr is not None:
         L.hpcla_csr_destroy(A._csr)
         A._csr = None
@@ -294,6 +305,32 @@ def build_vector_plan(A: HPCSparseMatrix, x: HPCVector) -> VectorPlan:
     return VectorPlan(ph.value, A.backend.Ti, x.local_size)
 
 
+def import_vector_plan(A: HPCSparseMatrix, x: HPCVector, send_rank_ids, send_indices, recv_rank_ids, recv_perm, local_src_indices,
+                       local_dst_indices, n_gathered: int) -> VectorPlan:
+    """Adopt a VectorPlan that was built elsewhere — the route of the Julia binding, which hands the plan the reference
+    itself built (src/sparse.jl:1875-1984; fields of src/vectors.jl:229-251, index arrays in Ti width, 1-based) to
+    hpcla_plan_import — and memoise it under the reference's cache key, so that `A * x` uses it."""
+    L = _lib.lib()
+    Ti = np.dtype(A.backend.Ti)
+    comm = A.backend.comm
+    sids = np.ascontiguousarray(send_rank_ids, dtype=np.int64)
+    rids = np.ascontiguousarray(recv_rank_ids, dtype=np.int64)
+    sidx = [np.ascontiguousarray(a, dtype=Ti) for a in send_indices]
+    rprm = [np.ascontiguousarray(a, dtype=Ti) for a in recv_perm]
+    slen = np.array([len(a) for a in sidx], dtype=np.int64)
+    rlen = np.array([len(a) for a in rprm], dtype=np.int64)
+    lsrc = np.ascontiguousarray(local_src_indices, dtype=Ti)
+    ldst = np.ascontiguousarray(local_dst_indices, dtype=Ti)
+    ph = ctypes.c_void_p()
+    _lib.check(L.hpcla_plan_import(comm_rank(comm), comm_size(comm), _lib.itype_code(Ti), int(n_gathered), x.local_size, len(sids), _lib.ptr(sids),
+                                   _lib.ptr(slen), _lib.ptr_array(sidx), len(rids), _lib.ptr(rids), _lib.ptr(rlen), _lib.ptr_array(rprm), len(lsrc),
+                                   _lib.ptr(lsrc), _lib.ptr(ldst), ctypes.byref(ph)))
+    plan = VectorPlan(ph.value, Ti, x.local_size)
+    key = (_ensure_hash(A), x.structural_hash, A.backend.T.str, A.backend.Ti.str, _storage_tag(x), _comm_key(A.backend))
+    _vector_plan_cache[key] = plan
+    return plan
+
+
 def _storage_tag(x: HPCVector) -> str:
     return "Vector" if isinstance(x.v, np.ndarray) else "CuVector"
 
@@ -322,6 +359,10 @@ def clear_plan_cache() -> None:
     _vector_plan_cache.clear()
     _v._repartition_plan_cache.clear()
     _matrix_plan_cache.clear()
+    # operators are bound to plans: with the plans gone they would only be re-created under new plan ids, so they
+    # (gathered / send buffers, tile lists, compact tile data) are released here instead of living as long as A does
+    for A in list(_live_matrices):
+        _drop_bound_ops(A)
 
 
 def cache_sizes() -> Dict[str, int]:
@@ -367,9 +408,12 @@ def spmv_info(A: HPCSparseMatrix, x: HPCVector) -> Dict[str, int]:
     _lib.check(L.hpcla_csr_info(_csr_handle(A), ctypes.byref(nt), ctypes.byref(nl), ctypes.byref(var)))
     nr, ng, ne, win = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int()
     _lib.check(L.hpcla_csr_tile_classes(_csr_handle(A), ctypes.byref(nr), ctypes.byref(ng), ctypes.byref(ne), ctypes.byref(win)))
+    lists = (ctypes.c_int64 * 6)()
+    _lib.check(L.hpcla_spmv_tile_lists(op, lists))
     return {"tiles": nt.value, "long_rows": nl.value, "lanes_per_row": var.value, "rowwalk_tiles": nr.value, "general_tiles": ng.value,
             "empty_tiles": ne.value, "tile_window": win.value, "interior_tiles": ni.value, "boundary_tiles": nb.value,
-            "x_in_place": xin.value, "sends_contiguous": sc.value, "launches": int(L.hpcla_spmv_launch_count(op))}
+            "x_in_place": xin.value, "sends_contiguous": sc.value, "launches": int(L.hpcla_spmv_launch_count(op)),
+            "compact_tiles": int(lists[4]), "flat_chunks": int(lists[5]), "plain_interior_rowwalk_tiles": int(lists[0])}
 
 
 def _check_mul_args(A: HPCSparseMatrix, x: HPCVector):
@@ -425,6 +469,67 @@ def mul(y: HPCVector, A: HPCSparseMatrix, x: HPCVector) -> HPCVector:
         raise ValueError(f"DimensionMismatch: y holds {y.local_size} local rows, A has {A.nrows_local}")
     _run_multiply(A, x, y.v)
     return y
+
+
+class HostBuffer:
+    """Pinned host memory next to this rank's GPU (hpcla_host_alloc): `.array` is a numpy view of it.  For the host
+    sides of mul_staged; on a multi-socket box the copies then stay on the GPU's own NUMA node."""
+
+    def __init__(self, backend: HPCBackend, n: int, dtype=None):
+        dt = np.dtype(backend.T if dtype is None else dtype)
+        self._ctx = backend.ctx()
+        p = ctypes.c_void_p()
+        node = ctypes.c_int(-1)
+        nbytes = int(n) * dt.itemsize
+        _lib.check(_lib.lib().hpcla_host_alloc(self._ctx.handle, nbytes, ctypes.byref(p), ctypes.byref(node)))
+        self.ptr = p.value
+        self.numa_node = node.value
+        raw = (ctypes.c_byte * max(nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=dt, count=int(n))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            _lib.lib().hpcla_host_free(self._ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_buffer(backend: HPCBackend, n: int, dtype=None) -> HostBuffer:
+    return HostBuffer(backend, n, dtype)
+
+
+def mul_graph(y: HPCVector, A: HPCSparseMatrix, x: HPCVector) -> HPCVector:
+    """mul!(y, A, x) replayed from a CUDA graph bound to these x.v / y.v (hpcla_spmv_graph_capture / _launch): the first
+    call with a given (x.v, y.v) runs one plain multiply (so every lazily configured kernel attribute is set) and then
+    captures; later calls are one graph launch.  NCCL world or a single rank.  Collective."""
+    _check_mul_args(A, x)
+    if y.local_size != A.nrows_local:
+        raise ValueError(f"DimensionMismatch: y holds {y.local_size} local rows, A has {A.nrows_local}")
+    L = _lib.lib()
+    op = _bound_op(A, get_vector_plan(A, x), x)
+    stream = _current_stream(A.backend)
+    key = (op, _lib.ptr(x.v), _lib.ptr(y.v))
+    if A._graphs.get("bound") != key:
+        _lib.check(L.hpcla_spmv_run(op, _lib.ptr(x.v), _lib.ptr(y.v), stream))
+        _lib.check(L.hpcla_spmv_graph_capture(op, _lib.ptr(x.v), _lib.ptr(y.v), stream))
+        A._graphs["bound"] = key
+    _lib.check(L.hpcla_spmv_graph_launch(op, stream))
+    return y
+
+
+def spmv_timeline(A: HPCSparseMatrix, x: HPCVector) -> Dict[str, float]:
+    """Timeline of the most recent multiply (operators created under HPCLA_TIMELINE=1): milliseconds from 'x ready' to
+    the end of the halo exchange, of the boundary tiles, of the interior tiles and of the call."""
+    op = _bound_op(A, get_vector_plan(A, x), x)
+    out = (ctypes.c_double * 4)()
+    _lib.check(_lib.lib().hpcla_spmv_timeline(op, out))
+    return {"exchange_ms": out[0], "boundary_ms": out[1], "interior_ms": out[2], "end_ms": out[3]}
 
 
 def mul_staged(y: HPCVector, A: HPCSparseMatrix, x: HPCVector, x_host, y_host) -> HPCVector:
@@ -607,16 +712,19 @@ def to_backend(obj, backend: HPCBackend):
 # ---------------------------------------------------------------------------------------------------------------
 # CG (a user-level composition in the reference; here one library call, no host sync per iteration)
 # ---------------------------------------------------------------------------------------------------------------
-def cg(A: HPCSparseMatrix, b: HPCVector, iters: int):
+def cg(A: HPCSparseMatrix, b: HPCVector, iters: int, x: Optional[HPCVector] = None, work=None):
     """Fixed-iteration conjugate gradients, x0 = 0.  Returns (x, rr_history) with rr_history[k] = dot(r, r) after
-    iteration k+1."""
+    iteration k+1.  x / work (3 * local_size elements of device scratch): optional caller-owned buffers — with
+    HPCLA_CG_GRAPH=1 the whole loop is one CUDA graph that is re-used as long as b, x, work and iters stay the same."""
     import torch
 
     _check_mul_args(A, b)
     plan = get_vector_plan(A, b)
     op = _bound_op(A, plan, b)
-    x = b.similar()
-    work = torch.empty(3 * b.local_size, dtype=_torch_dtype(A.backend.T), device=A.backend.torch_device())
+    if x is None:
+        x = b.similar()
+    if work is None:
+        work = torch.empty(3 * b.local_size, dtype=_torch_dtype(A.backend.T), device=A.backend.torch_device())
     hist = np.zeros(max(iters, 1), dtype=np.float64)
     _lib.check(_lib.lib().hpcla_cg(op, _lib.ptr(b.v), _lib.ptr(x.v), _lib.ptr(work), int(iters), _lib.ptr(hist), _current_stream(A.backend)))
     return x, hist[:iters]

@@ -1,65 +1,27 @@
-"""Deterministic synthetic inputs — python front-end of include/hpcla_synth.h.
+"""Deterministic synthetic inputs as HPCSparseMatrix / HPCVector objects.
 
-Used by tests, bench.py and the CPU baseline alike, so that the GPU path and the oracle see identical bits.  Each rank
-generates only its own rows (HPCSparseMatrix_local route, src/sparse.jl:454): nothing global is ever materialised.
+The generators themselves live in their own host-only library (hpcla_synth/, include/hpcla_synth.h) shared with the
+CPU oracle and the CPU reference arm, so that the GPU path and the checker see identical bits.  Each rank generates
+only its own rows (HPCSparseMatrix_local route, src/sparse.jl:454): nothing global is ever materialised.
 """
 from __future__ import annotations
 
-import numpy as np
+import os
+import sys
 
-from . import _lib
-from .backends import HPCBackend, comm_rank, comm_size
-from .sparse import HPCSparseMatrix
-from .vectors import HPCVector, uniform_partition
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
 
-LAPLACE2D_5PT, POISSON3D_7PT, STENCIL3D_27PT = 0, 1, 2
-X_SEED = 0x5EED
+import hpcla_synth as _gen  # noqa: E402
+from hpcla_synth import (  # noqa: E402,F401
+    LAPLACE2D_5PT, POISSON3D_7PT, POWERLAW_MAX_LEN, POWERLAW_SEED, STENCIL3D_27PT, X_SEED, powerlaw_local, stencil_local, stencil_rows,
+    vector_at, vector_local,
+)
 
-
-def _grid(N):
-    """N: an int (square / cubic grid) or a tuple (nx, ny[, nz])."""
-    if isinstance(N, (int, np.integer)):
-        return int(N), int(N), int(N)
-    g = tuple(int(v) for v in N)
-    return (g[0], g[1], 1) if len(g) == 2 else g
-
-
-def stencil_rows(kind: int, N) -> int:
-    return int(_lib.lib().hpcla_synth_stencil_rows(kind, *_grid(N)))
-
-
-def stencil_local(kind: int, N, row_begin: int, row_end: int, T, Ti):
-    """Rows [row_begin, row_end) (0-based) -> (rowptr 1-based, GLOBAL columns 1-based, values)."""
-    L = _lib.lib()
-    T, Ti = np.dtype(T), np.dtype(Ti)
-    nnz = int(L.hpcla_synth_stencil_nnz(kind, *_grid(N), row_begin, row_end))
-    if Ti == np.int32 and nnz >= 2**31 - 1:
-        raise _lib.HPCLAError("local nnz does not fit Int32 row pointers")
-    rowptr = np.empty(row_end - row_begin + 1, dtype=Ti)
-    cols = np.empty(nnz, dtype=Ti)
-    vals = np.empty(nnz, dtype=T)
-    _lib.check(L.hpcla_synth_stencil_fill(kind, *_grid(N), _lib.dtype_code(T), _lib.itype_code(Ti), row_begin, row_end, _lib.ptr(rowptr), _lib.ptr(cols), _lib.ptr(vals)))
-    return rowptr, cols, vals
-
-
-def powerlaw_local(n: int, seed: int, max_len: int, row_begin: int, row_end: int, T, Ti):
-    L = _lib.lib()
-    T, Ti = np.dtype(T), np.dtype(Ti)
-    nnz = int(L.hpcla_synth_powerlaw_nnz(n, seed, max_len, row_begin, row_end))
-    if Ti == np.int32 and nnz >= 2**31 - 1:
-        raise _lib.HPCLAError("local nnz does not fit Int32 row pointers")
-    rowptr = np.empty(row_end - row_begin + 1, dtype=Ti)
-    cols = np.empty(nnz, dtype=Ti)
-    vals = np.empty(nnz, dtype=T)
-    _lib.check(L.hpcla_synth_powerlaw_fill(n, seed, max_len, _lib.dtype_code(T), _lib.itype_code(Ti), row_begin, row_end, _lib.ptr(rowptr), _lib.ptr(cols), _lib.ptr(vals)))
-    return rowptr, cols, vals
-
-
-def vector_local(T, seed: int, begin: int, end: int) -> np.ndarray:
-    """x[g] = 2u(g) - 1 for g in [begin, end) (0-based)."""
-    out = np.empty(end - begin, dtype=np.dtype(T))
-    _lib.check(_lib.lib().hpcla_synth_vector(_lib.dtype_code(T), seed, begin, end, _lib.ptr(out)))
-    return out
+from .backends import HPCBackend, comm_rank, comm_size  # noqa: E402
+from .sparse import HPCSparseMatrix  # noqa: E402
+from .vectors import HPCVector, uniform_partition  # noqa: E402
 
 
 def _my_rows(n: int, backend: HPCBackend):
@@ -75,7 +37,7 @@ def stencil_matrix(kind: int, N, backend: HPCBackend) -> HPCSparseMatrix:
     return HPCSparseMatrix.from_local(rowptr, cols, vals, n, backend, col_partition=part)
 
 
-def powerlaw_matrix(n: int, backend: HPCBackend, seed: int = 0xC4, max_len: int = 1_000_000) -> HPCSparseMatrix:
+def powerlaw_matrix(n: int, backend: HPCBackend, seed: int = POWERLAW_SEED, max_len: int = POWERLAW_MAX_LEN) -> HPCSparseMatrix:
     part, b, e = _my_rows(n, backend)
     rowptr, cols, vals = powerlaw_local(n, seed, max_len, b, e, backend.T, backend.Ti)
     return HPCSparseMatrix.from_local(rowptr, cols, vals, n, backend, col_partition=part)

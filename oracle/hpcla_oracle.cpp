@@ -513,3 +513,232 @@ extern "C" int orc_bench_spmv(const OrcPlans* W, int dtype, int itype, const i64
     ORC_CASE(2, 1, c128, int64_t)
     return 1;
 }
+
+// ------------------------------------------------------------------------------------------------
+// CPU reference arm on a SYNTHETIC workload, generated inside the workers.
+// Same per-repetition work as bench_worker above, but every worker (= one reference MPI rank)
+// allocates, generates and first-touches its own row block, vectors and buffers from its own
+// thread (optionally pinned to one core), the way P MPI processes would: on a multi-socket host the
+// pages then live next to the core that streams them.  The generators are the ones of
+// include/hpcla_synth.h, handed in as function pointers (this library does not link the other).
+//   kind 0..2: stencils on an nx x ny x nz grid;  kind 3: power-law rows (n = nx, seed, max_len)
+//   op 0: `inner` multiplies per repetition (inner = ncols models the reference's column loop for
+//         A * B::HPCMatrix, src/sparse.jl:2398-2403);
+//   op 1: one CG iteration per repetition (q = A*p; alpha = rr / dot(p,q); x += alpha p;
+//         r -= alpha q; rr' = dot(r,r); p = r + (rr'/rr) p — dot = local sum + Allreduce,
+//         src/vectors.jl:798-812), real types only.
+// times_out[rep]: wall seconds; nnz_out: global stored entries; ynorm2_out: sum |y|^2 of the last
+// multiply (a cross-check value).
+// ------------------------------------------------------------------------------------------------
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
+
+#include <cstdlib>
+
+typedef i64 (*fn_stencil_nnz)(int, i64, i64, i64, i64, i64);
+typedef int (*fn_stencil_fill)(int, i64, i64, i64, int, int, i64, i64, void*, void*, void*);
+typedef i64 (*fn_powerlaw_nnz)(i64, uint64_t, i64, i64, i64);
+typedef int (*fn_powerlaw_fill)(i64, uint64_t, i64, int, int, i64, i64, void*, void*, void*);
+typedef int (*fn_vector)(int, uint64_t, i64, i64, void*);
+typedef void (*fn_set_threads)(int);
+
+struct SynthJob {
+    fn_stencil_nnz stencil_nnz;
+    fn_stencil_fill stencil_fill;
+    fn_powerlaw_nnz powerlaw_nnz;
+    fn_powerlaw_fill powerlaw_fill;
+    fn_vector vector;
+    fn_set_threads set_threads;
+    int kind, dtype, itype, op, pin;
+    i64 nx, ny, nz, n, P, warmup, reps, inner, max_len;
+    uint64_t seed, x_seed;
+    std::vector<i64> partition;
+    // shared between the workers
+    std::vector<std::vector<i64>> col_indices;
+    std::vector<const i64*> ci_ptr;
+    std::vector<i64> ncc;
+    OrcPlans* plans = nullptr;
+    std::vector<i64> nnz;
+    std::vector<double> ynorm2, red;  // per-worker partial sums (Allreduce stand-in)
+    std::atomic<int> failed{0};
+    double* times_out;
+};
+
+static inline double norm2_of(float v) { return (double)v * (double)v; }
+static inline double norm2_of(double v) { return v * v; }
+static inline double norm2_of(c128 v) { return v.re * v.re + v.im * v.im; }
+
+template <class T> struct Axpy {
+    static void run(T*, const T*, double, i64) {}
+    static double dot(const T*, const T*, i64) { return 0.0; }
+    static void xpby(T*, const T*, double, i64) {}
+};
+template <> struct Axpy<float> {
+    static void run(float* y, const float* x, double a, i64 n) { for (i64 i = 0; i < n; ++i) y[i] = y[i] + (float)a * x[i]; }
+    static double dot(const float* x, const float* y, i64 n) { float s = 0; for (i64 i = 0; i < n; ++i) s += x[i] * y[i]; return (double)s; }
+    static void xpby(float* p, const float* r, double b, i64 n) { for (i64 i = 0; i < n; ++i) p[i] = r[i] + (float)b * p[i]; }
+};
+template <> struct Axpy<double> {
+    static void run(double* y, const double* x, double a, i64 n) { for (i64 i = 0; i < n; ++i) y[i] = y[i] + a * x[i]; }
+    static double dot(const double* x, const double* y, i64 n) { double s = 0; for (i64 i = 0; i < n; ++i) s += x[i] * y[i]; return s; }
+    static void xpby(double* p, const double* r, double b, i64 n) { for (i64 i = 0; i < n; ++i) p[i] = r[i] + b * p[i]; }
+};
+
+template <class T, class Ti>
+static void synth_worker(SynthJob* J, i64 rank, SpinBarrier* bar, std::vector<std::vector<std::vector<T>>>* sendbufs) {
+    if (J->pin) {
+        const long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET((int)(rank % (ncpu > 0 ? ncpu : 1)), &set);
+        pthread_setaffinity_np(pthread_self(), sizeof set, &set);  // best effort
+    }
+    J->set_threads(1);
+    const i64 rb = J->partition[rank] - 1, re = J->partition[rank + 1] - 1, nrows = re - rb;
+    const i64 nnz = J->kind == 3 ? J->powerlaw_nnz(J->n, J->seed, J->max_len, rb, re) : J->stencil_nnz(J->kind, J->nx, J->ny, J->nz, rb, re);
+    J->nnz[rank] = nnz;
+    Ti* rowptr = (Ti*)std::malloc(sizeof(Ti) * (size_t)(nrows + 1));
+    Ti* cols = (Ti*)std::malloc(sizeof(Ti) * (size_t)std::max<i64>(nnz, 1));
+    T* vals = (T*)std::malloc(sizeof(T) * (size_t)std::max<i64>(nnz, 1));
+    int rc = J->kind == 3 ? J->powerlaw_fill(J->n, J->seed, J->max_len, J->dtype, J->itype, rb, re, rowptr, cols, vals)
+                          : J->stencil_fill(J->kind, J->nx, J->ny, J->nz, J->dtype, J->itype, rb, re, rowptr, cols, vals);
+    if (rc || !rowptr || !cols || !vals) J->failed.store(1);
+    // src/sparse.jl:501, 137-144: col_indices = unique!(sort(copy(cols))); colval = searchsortedfirst(col_indices, col)
+    {
+        std::vector<i64>& ci = J->col_indices[rank];
+        ci.assign(cols, cols + nnz);
+        std::sort(ci.begin(), ci.end());
+        ci.erase(std::unique(ci.begin(), ci.end()), ci.end());
+        ci.shrink_to_fit();
+        const i64 ncc = (i64)ci.size();
+        for (i64 k = 0; k < nnz; ++k) cols[k] = (Ti)searchsortedfirst(ci.data(), ncc, (i64)cols[k]);
+        J->ncc[rank] = ncc;
+        J->ci_ptr[rank] = ci.data();
+    }
+    bar->wait();
+    if (rank == 0) J->plans = orc_plans_build(J->P, J->ci_ptr.data(), J->ncc.data(), J->partition.data());  // src/sparse.jl:1875-1984
+    bar->wait();
+    const RankPlan& p = J->plans->ranks[rank];
+    std::vector<std::vector<T>>& mine = (*sendbufs)[rank];
+    mine.resize(p.send_rank_ids.size());
+    for (size_t i = 0; i < mine.size(); ++i) mine[i].assign(p.send_indices[i].size(), zero_of<T>());
+    std::vector<T> gc((size_t)p.n_gathered, zero_of<T>()), g((size_t)p.n_gathered, zero_of<T>());
+    std::vector<T> x((size_t)nrows), y((size_t)nrows, zero_of<T>());
+    J->vector(J->dtype, J->x_seed, rb, re, x.data());
+    std::vector<T> cg_x, cg_r;  // CG state (op 1): p = x (the multiplied vector), q = y
+    double rr = 0.0;
+    auto allreduce = [&](double local) {  // Allreduce(+): everybody publishes, everybody adds in rank order
+        J->red[rank] = local;
+        bar->wait();
+        double s = 0.0;
+        for (i64 r = 0; r < J->P; ++r) s += J->red[r];
+        bar->wait();
+        return s;
+    };
+    if (J->op == 1) {
+        cg_x.assign((size_t)nrows, zero_of<T>());
+        cg_r = x;
+        rr = allreduce(Axpy<T>::dot(cg_r.data(), cg_r.data(), nrows));
+    }
+    auto multiply = [&]() {  // execute_plan! (src/vectors.jl:394-463) + the row loop (src/sparse.jl:2055-2066)
+        for (size_t i = 0; i < p.local_src.size(); ++i) gc[p.local_dst[i] - 1] = x[p.local_src[i] - 1];
+        for (size_t i = 0; i < p.send_rank_ids.size(); ++i) {
+            const std::vector<i64>& idx = p.send_indices[i];
+            T* buf = mine[i].data();
+            for (size_t k = 0; k < idx.size(); ++k) buf[k] = x[idx[k] - 1];
+        }
+        bar->wait();  // stands for the completion of Isend/Irecv (Waitall, vectors.jl:446)
+        for (size_t i = 0; i < p.recv_rank_ids.size(); ++i) {
+            const i64 r = p.recv_rank_ids[i];
+            const RankPlan& q = J->plans->ranks[r];
+            const size_t slot = std::find(q.send_rank_ids.begin(), q.send_rank_ids.end(), rank) - q.send_rank_ids.begin();
+            const T* buf = (*sendbufs)[r][slot].data();
+            const std::vector<i64>& perm = p.recv_perm[i];
+            for (size_t k = 0; k < perm.size(); ++k) gc[perm[k] - 1] = buf[k];
+        }
+        bar->wait();  // nobody repacks while a peer still reads its buffer
+        std::memcpy((void*)g.data(), (const void*)gc.data(), gc.size() * sizeof(T));  // vectors.jl:460 via :163
+        spmv_rows<T, Ti>(0, nrows, rowptr, cols, vals, g.data(), y.data());
+    };
+    for (i64 it = 0; it < J->warmup + J->reps; ++it) {
+        bar->wait();
+        auto t0 = std::chrono::steady_clock::now();
+        if (J->op == 0) {
+            for (i64 k = 0; k < J->inner; ++k) multiply();
+        } else {
+            multiply();  // q = A p
+            const double pq = allreduce(Axpy<T>::dot(x.data(), y.data(), nrows));
+            const double alpha = rr / pq;
+            Axpy<T>::run(cg_x.data(), x.data(), alpha, nrows);
+            Axpy<T>::run(cg_r.data(), y.data(), -alpha, nrows);
+            const double rr_new = allreduce(Axpy<T>::dot(cg_r.data(), cg_r.data(), nrows));
+            Axpy<T>::xpby(x.data(), cg_r.data(), rr_new / rr, nrows);
+            rr = rr_new;
+        }
+        bar->wait();
+        auto t1 = std::chrono::steady_clock::now();
+        if (rank == 0 && it >= J->warmup) J->times_out[it - J->warmup] = std::chrono::duration<double>(t1 - t0).count();
+    }
+    double s = 0.0;
+    for (i64 i = 0; i < nrows; ++i) s += norm2_of(y[(size_t)i]);
+    J->ynorm2[rank] = s;
+    bar->wait();
+    std::free(rowptr);
+    std::free(cols);
+    std::free(vals);
+}
+
+template <class T, class Ti>
+static int synth_run(SynthJob* J) {
+    std::vector<std::vector<std::vector<T>>> sendbufs((size_t)J->P);
+    SpinBarrier bar((int)J->P);
+    std::vector<std::thread> th;
+    for (i64 r = 0; r < J->P; ++r) th.emplace_back(synth_worker<T, Ti>, J, r, &bar, &sendbufs);
+    for (auto& t : th) t.join();
+    return J->failed.load();
+}
+
+extern "C" int orc_bench_synth(const void* const* fns6, int kind, i64 nx, i64 ny, i64 nz, uint64_t seed, i64 max_len, uint64_t x_seed, int dtype,
+                               int itype, i64 P, int pin, int op, i64 inner, i64 warmup, i64 reps, double* times_out, i64* nnz_out,
+                               double* ynorm2_out) {
+    SynthJob J;
+    J.stencil_nnz = (fn_stencil_nnz)fns6[0];
+    J.stencil_fill = (fn_stencil_fill)fns6[1];
+    J.powerlaw_nnz = (fn_powerlaw_nnz)fns6[2];
+    J.powerlaw_fill = (fn_powerlaw_fill)fns6[3];
+    J.vector = (fn_vector)fns6[4];
+    J.set_threads = (fn_set_threads)fns6[5];
+    J.kind = kind, J.dtype = dtype, J.itype = itype, J.op = op, J.pin = pin;
+    J.nx = nx, J.ny = ny, J.nz = nz, J.P = P, J.warmup = warmup, J.reps = reps, J.inner = inner < 1 ? 1 : inner, J.max_len = max_len;
+    J.seed = seed, J.x_seed = x_seed;
+    J.n = kind == 3 ? nx : (kind == 0 ? nx * ny : nx * ny * nz);
+    if (P < 1 || J.n < P || reps < 1 || (op == 1 && dtype == 2)) return 2;
+    J.partition.resize((size_t)P + 1);
+    orc_uniform_partition(J.n, P, J.partition.data());
+    J.col_indices.resize((size_t)P);
+    J.ci_ptr.assign((size_t)P, nullptr);
+    J.ncc.assign((size_t)P, 0);
+    J.nnz.assign((size_t)P, 0);
+    J.ynorm2.assign((size_t)P, 0.0);
+    J.red.assign((size_t)P, 0.0);
+    J.times_out = times_out;
+    int rc = 1;
+#undef ORC_CASE
+#define ORC_CASE(D, I, T, Ti) \
+    if (dtype == D && itype == I) rc = synth_run<T, Ti>(&J);
+    ORC_CASE(0, 0, float, int32_t)
+    ORC_CASE(0, 1, float, int64_t)
+    ORC_CASE(1, 0, double, int32_t)
+    ORC_CASE(1, 1, double, int64_t)
+    ORC_CASE(2, 0, c128, int32_t)
+    ORC_CASE(2, 1, c128, int64_t)
+#undef ORC_CASE
+    if (J.plans) orc_plans_free(J.plans);
+    i64 nnz = 0;
+    double yn = 0.0;
+    for (i64 r = 0; r < P; ++r) nnz += J.nnz[(size_t)r], yn += J.ynorm2[(size_t)r];
+    if (nnz_out) *nnz_out = nnz;
+    if (ynorm2_out) *ynorm2_out = yn;
+    return rc;
+}

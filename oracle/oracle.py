@@ -72,6 +72,9 @@ def lib() -> ctypes.CDLL:
         L.orc_transpose_get.argtypes = [vp, i64, ci, vp]
         L.orc_bench_spmv.argtypes = [vp, ci, ci, vp, vp, vp, vp, vp, vp, i64, i64, vp]
         L.orc_bench_spmv.restype = ci
+        u64 = ctypes.c_uint64
+        L.orc_bench_synth.argtypes = [vp, ci, i64, i64, i64, u64, i64, u64, ci, ci, i64, ci, ci, i64, i64, i64, vp, vp, vp]
+        L.orc_bench_synth.restype = ci
         _lib = L
     return _lib
 
@@ -267,6 +270,19 @@ def spmv_local(m: LocalMatrix, gathered: np.ndarray) -> np.ndarray:
     y = np.empty(m.nrows_local, dtype=m.nzval.dtype)
     g = np.ascontiguousarray(gathered, dtype=m.nzval.dtype)
     getattr(lib(), name)(m.nrows_local, _p(m.rowptr), _p(m.colval), _p(m.nzval), _p(g), _p(y))
+    return y
+
+
+def spmv_csr(rowptr, colval, nzval, x) -> np.ndarray:
+    """The same row loop on bare arrays: y[r] = sum_j nzval[j] * x[colval[j]] (1-based rowptr / colval), left to right."""
+    rowptr = np.ascontiguousarray(rowptr)
+    colval = np.ascontiguousarray(colval, dtype=rowptr.dtype)
+    nzval = np.ascontiguousarray(nzval)
+    name = f"orc_spmv_{dtype_name(nzval.dtype)}_{itype_name(rowptr.dtype)}"
+    n = len(rowptr) - 1
+    y = np.empty(n, dtype=nzval.dtype)
+    xg = np.ascontiguousarray(x, dtype=nzval.dtype)
+    getattr(lib(), name)(n, _p(rowptr), _p(colval), _p(nzval), _p(xg), _p(y))
     return y
 
 
@@ -544,6 +560,30 @@ def bench_spmv(locals_: Sequence[LocalMatrix], x_locals: Sequence[np.ndarray], x
     if rc != 0:
         raise RuntimeError("orc_bench_spmv: unsupported type combination")
     return times, ys
+
+
+def bench_synth(kind: int, grid, dtype, itype, workers: int, warmup=1, reps=5, op="mul", inner=1, pin=True,
+                seed=0xC4, max_len=1_000_000, x_seed=0x5EED):
+    """CPU reference arm on a synthetic workload (orc_bench_synth): every worker thread (= one reference MPI rank)
+    generates and first-touches its own row block.  kind 0..2: stencil on grid (nx, ny, nz); kind 3: power-law rows,
+    n = grid[0].  op "mul": `inner` multiplies per repetition; op "cg": one CG iteration per repetition.
+    Returns (times[reps], nnz, sum |y|^2 of the last multiply)."""
+    import hpcla_synth  # the generators live in their own library (include/hpcla_synth.h)
+
+    S = hpcla_synth.lib()
+    fns = (ctypes.c_void_p * 6)(*[ctypes.cast(getattr(S, n), ctypes.c_void_p).value for n in (
+        "hpcla_synth_stencil_nnz", "hpcla_synth_stencil_fill", "hpcla_synth_powerlaw_nnz", "hpcla_synth_powerlaw_fill", "hpcla_synth_vector",
+        "hpcla_synth_set_threads")])
+    nx, ny, nz = (int(g) for g in grid)
+    times = np.zeros(reps, dtype=np.float64)
+    nnz = ctypes.c_int64(0)
+    yn = ctypes.c_double(0.0)
+    rc = lib().orc_bench_synth(fns, int(kind), nx, ny, nz, seed, max_len, x_seed, DTYPE_CODE[dtype_name(dtype)], ITYPE_CODE[itype_name(itype)],
+                               int(workers), int(bool(pin)), {"mul": 0, "cg": 1}[op], int(inner), int(warmup), int(reps), _p(times),
+                               ctypes.byref(nnz), ctypes.byref(yn))
+    if rc != 0:
+        raise RuntimeError(f"orc_bench_synth failed (status {rc})")
+    return times, int(nnz.value), float(yn.value)
 
 
 # ------------------------------------------------------------------------------------------------------------------

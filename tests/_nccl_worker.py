@@ -125,6 +125,64 @@ def main():
     sol, hist = la.cg(A, la.HPCVector.from_global(bh, b), 30)
     xo, ho = orc.cg(orc.distribute(G, 1, itype="i32"), bh, 30)
     assert relerr(sol.to_global(), xo) <= 1e-9 and np.allclose(hist, ho, rtol=1e-8)
+    # 4. the route the Julia binding takes: a communicator created OUTSIDE the library (ncclCommInitRank through ctypes,
+    #    as ext/HPCLinearAlgebraCUDAExt.jl:411-443 does) handed to hpcla_ctx_adopt_nccl, and a plan built by the reference's
+    #    algorithm (the oracle, in Ti width) handed to hpcla_plan_import
+    import ctypes
+
+    nccl = ctypes.CDLL("libnccl.so.2")
+
+    class NcclUniqueId(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_byte * 128)]
+
+    uid = NcclUniqueId()
+    if rank == 0:
+        assert nccl.ncclGetUniqueId(ctypes.byref(uid)) == 0
+    raw = la.comm_bcast(comm, bytes(uid.internal), 0)
+    ctypes.memmove(ctypes.byref(uid), raw, 128)
+    ext_comm = ctypes.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [ctypes.c_void_p, ctypes.c_int, NcclUniqueId, ctypes.c_int]
+    assert nccl.ncclCommInitRank(ctypes.byref(ext_comm), P, uid, rank) == 0
+    comm2 = la.CommMPI(nccl_comm=ext_comm.value)
+    for kind, N, T, Ti in [(1, 24, np.float64, np.int32), (2, 14, np.complex128, np.int64)]:
+        b2 = la.backend_cuda_mpi(T, Ti, comm=comm2, device=local_rank)
+        assert b2.ctx().world == "nccl"
+        n = S.stencil_rows(kind, N)
+        A = S.stencil_matrix(kind, N, b2)
+        x = S.vector(n, b2)
+        rp, c, v = S.stencil_local(kind, N, 0, n, T, Ti)
+        G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+        olocs = orc.distribute(G, P, itype="i32" if Ti == np.int32 else "i64")
+        xp = orc.uniform_partition(n, P)
+        oplan = orc.vector_plans(olocs, xp)[rank]
+        plan = la.sparse.import_vector_plan(A, x, oplan.send_rank_ids, oplan.send_indices, oplan.recv_rank_ids, oplan.recv_perm,
+                                            oplan.local_src_indices, oplan.local_dst_indices, oplan.n_gathered)
+        assert la.get_vector_plan(A, x) is plan  # memoised under the reference's key
+        xh = S.vector_local(T, S.X_SEED, 0, n)
+        ref = orc.matvec(olocs, xh)
+        y = A * x
+        assert relerr(y.to_global(), ref) <= TOL[np.dtype(T)], ("adopted comm + imported plan", kind)
+        g = la.execute_plan(plan, A, x)
+        torch.cuda.synchronize()
+        W = orc.PlanWorld(olocs, xp)
+        assert np.array_equal(g.cpu().numpy(), W.execute(orc.split_vector(xh, xp))[rank])
+        W.close()
+        # the same multiply replayed from a CUDA graph (captured grouped ncclSend/ncclRecv)
+        yg = la.HPCVector.zeros(b2, n)
+        for _ in range(3):
+            yg.v.zero_()
+            la.mul_graph(yg, A, x)
+            torch.cuda.synchronize()
+            assert torch.equal(yg.v, y.v), ("graph replay", kind)
+    # 5. irregular matrix (nnz-split kernel) with ghosts, and a stencil-like matrix whose general tiles border ghost columns
+    b = la.backend_cuda_mpi(np.float32, np.int32, comm=comm, device=local_rank)
+    n = 40000
+    A = S.powerlaw_matrix(n, b, max_len=20000)
+    x = S.vector(n, b)
+    rp, c, v = S.powerlaw_local(n, S.POWERLAW_SEED, 20000, 0, n, np.float32, np.int32)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    ref = orc.matvec(orc.distribute(G, P, itype="i32"), S.vector_local(np.float32, S.X_SEED, 0, n))
+    assert relerr((A * x).to_global(), ref) <= 1e-5, "power-law rows over NCCL"
     dist.barrier()
     print("NCCL_OK", flush=True)
     dist.destroy_process_group()

@@ -237,3 +237,61 @@ def test_reference_product_fixtures():
             else:
                 assert np.max(np.abs(orc.matmat(lA, fx["Bdense"]) - fx["C"])) < fx["tol"], fx["name"]
                 assert np.max(np.abs(orc.matmat(orc.transpose(lA), fx["Bdense"]) - fx["CT"])) < fx["tol"], fx["name"]
+
+
+def test_rowcheck_agrees_with_the_full_oracle():
+    """oracle/rowcheck.py (rows regenerated from the generators) == the distributed oracle, bit for bit, on every rank's
+    boundary planes and random runs; and it notices a single wrong ghost value."""
+    import hpcla_synth as S
+    from oracle import rowcheck as rc
+
+    for kind, grid, T, Ti in [(1, (14, 12, 10), np.float64, np.int32), (2, (9, 9, 9), np.complex128, np.int32), (0, (40, 30, 1), np.float64, np.int64),
+                              (3, (20000, 1, 1), np.float32, np.int32)]:
+        n = rc.n_rows(kind, grid)
+        rp, c, v = rc._rows(kind, grid, 0, n, T, Ti)
+        A = sp.csr_matrix((v, c.astype(np.int64) - 1, rp.astype(np.int64) - 1), shape=(n, n))
+        x = S.vector_local(T, S.X_SEED, 0, n)
+        locs = orc.distribute(A, 1, itype="i32" if Ti == np.int32 else "i64")
+        y = orc.matvec(locs, x)
+        for P in (1, 3):
+            part = orc.uniform_partition(n, P)
+            for r in range(P):
+                b, e = int(part[r]) - 1, int(part[r + 1]) - 1
+                rows, worst, exact, nr = rc.check_rows(kind, grid, b, e, y[b:e], T, Ti, seed=r, run=64)
+                assert worst == 0.0 and exact == nr and rows > 0
+        if kind != 3:
+            yT = orc.matvec(orc.transpose(locs), x)
+            rows, worst, exact, nr = rc.check_rows(kind, grid, 0, n, yT, T, Ti, transpose=True, run=64)
+            assert worst == 0.0 and exact == nr
+        # a multiply that used x[j] + 1 for one ghost of rank 1 (a mis-routed halo element) is caught
+        if kind == 1:
+            part = orc.uniform_partition(n, 2)
+            b, e = int(part[1]) - 1, int(part[2]) - 1
+            xb = x.copy()
+            xb[b - 3] += 1.0  # an element owned by rank 0 that rank 1 reads as a ghost
+            yb = A @ xb
+            _, worst, exact, nr = rc.check_rows(kind, grid, b, e, yb[b:e], T, Ti, seed=1, run=64)
+            assert worst > 1e-6 and exact < nr
+
+
+def test_reference_arm_on_synthetic_workloads():
+    """orc_bench_synth (the CPU reference arm: every worker generates and first-touches its own block) computes the same
+    y as the oracle on a matrix built outside it, for every workload kind; and its CG leg runs."""
+    import hpcla_synth as S
+
+    for kind, grid, T, Ti in [(1, (12, 10, 8), np.float64, np.int32), (2, (9, 9, 9), np.complex128, np.int64), (3, (5000, 1, 1), np.float32, np.int32),
+                              (0, (30, 20, 1), np.float64, np.int64)]:
+        n = grid[0] if kind == 3 else S.stencil_rows(kind, grid)
+        t, nnz, yn = orc.bench_synth(kind, grid, T, Ti, workers=3, warmup=1, reps=2)
+        if kind == 3:
+            rp, c, v = S.powerlaw_local(n, S.POWERLAW_SEED, S.POWERLAW_MAX_LEN, 0, n, T, Ti)
+        else:
+            rp, c, v = S.stencil_local(kind, grid, 0, n, T, Ti)
+        A = sp.csr_matrix((v, c.astype(np.int64) - 1, rp.astype(np.int64) - 1), shape=(n, n))
+        y = orc.matvec(orc.distribute(A, 1, itype="i32" if Ti == np.int32 else "i64"), S.vector_local(T, S.X_SEED, 0, n))
+        assert nnz == A.nnz and len(t) == 2 and np.all(t > 0)
+        assert abs(yn - float(np.sum(np.abs(y.astype(np.complex128)) ** 2))) <= 1e-9 * yn
+    t, nnz, _ = orc.bench_synth(1, (12, 10, 8), np.float64, np.int32, workers=4, reps=3, op="cg")
+    assert len(t) == 3 and np.all(t > 0)
+    t, nnz, _ = orc.bench_synth(1, (12, 10, 8), np.float64, np.int32, workers=2, reps=2, inner=4)
+    assert len(t) == 2
