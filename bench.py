@@ -72,6 +72,8 @@ def workload_spec(name: str, n_gpus: int) -> dict:
         return dict(name=f"poisson3d_7pt {g[0]}x{g[1]}x{g[2]} times a dense {k}-column HPCMatrix", kind=1, grid=g, T="f64", Ti="i32", op="spmm", scaling="weak", ncols=k)
     if name == "cg-512":
         g = (512, 512, 512) if n_gpus == 8 else weak_grid(n_gpus)
+        if os.environ.get("HPCLA_BENCH_CG_GRID"):  # e.g. 512: the 8-GPU problem on fewer GPUs ("vs the 1-GPU run")
+            g = (int(os.environ["HPCLA_BENCH_CG_GRID"]),) * 3
         return dict(name=f"CG on poisson3d_7pt {g[0]}x{g[1]}x{g[2]}", kind=1, grid=g, T="f64", Ti="i32", op="cg", scaling="weak")
     raise SystemExit(f"unknown workload {name!r}")
 

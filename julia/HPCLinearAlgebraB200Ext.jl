@@ -1,7 +1,9 @@
 # HPCLinearAlgebraB200Ext.jl — the reference-side binding of libhpcla_b200.so.
 #
-# STATUS: written against the reference's sources (file:line cited below) but NEVER EXECUTED: this image has no
-# julia, no MPI and no CUDA.jl.  It is the stub a maintainer would add next to ext/HPCLinearAlgebraCUDAExt.jl;
+# STATUS: EXPERIMENTAL — written against the reference's sources (file:line cited below) but NEVER EXECUTED: this image
+# has no julia, no MPI and no CUDA.jl.  The C-ABI route it takes (hpcla_ctx_adopt_nccl / hpcla_ctx_init_nccl,
+# hpcla_csr_create, hpcla_plan_import with the reference-built plan, hpcla_spmv_create / run) is exercised call for call
+# by tests/test_gpu_round2.py::test_plan_import_route and tests/_nccl_worker.py (section 4) from Python.  It is the stub a maintainer would add next to ext/HPCLinearAlgebraCUDAExt.jl;
 # INTEGRATION.md walks through it.  The python mirror under linearalgebrampi.jl_b200/ drives the very same C ABI
 # and is what the tests and benchmarks run.
 #
@@ -72,13 +74,33 @@ mutable struct BoundOp
     csr::Ptr{Cvoid}
     plan::Ptr{Cvoid}
     op::Ptr{Cvoid}
-    roots::Any   # keeps the borrowed arrays alive for the lifetime of the handles (cf. ext:549-551)
+    key::Any
 end
-const _bound = Dict{Any,BoundOp}()
+# Keyed by the matrix OBJECT (weakly): the handles borrow A.rowptr_target / A.colval_target / A.nzval, which live exactly
+# as long as A does, so nothing is rooted here and nothing outlives its matrix (the previous version kept every multiplied
+# matrix's arrays alive until clear_bound!).  The inner key is the reference's plan-cache key (src/sparse.jl:1994): a
+# structural change drops A.structural_hash (src/indexing.jl:1291-1294), hence yields a new key and a new handle.
+const _bound = WeakKeyDict{Any,Dict{Any,BoundOp}}()
+
+# Frees the library handles of one matrix.  Only local work (cudaFree + stream synchronisation), no collective — safe in a
+# finalizer, unlike destroying an NCCL communicator (ext/HPCLinearAlgebraCUDAExt.jl:9-10).
+function _release!(ops::Dict{Any,BoundOp})
+    for b in values(ops)
+        @ccall libhpcla.hpcla_spmv_destroy(b.op::Ptr{Cvoid})::Cvoid
+        @ccall libhpcla.hpcla_plan_destroy(b.plan::Ptr{Cvoid})::Cvoid
+        @ccall libhpcla.hpcla_csr_destroy(b.csr::Ptr{Cvoid})::Cvoid
+    end
+    empty!(ops)
+end
 
 function _bind(A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T}, plan::VectorPlan{T,Ti}) where {T,Ti,B<:CuB}
-    key = (_ensure_hash(A), x.structural_hash, T, Ti, objectid(A.nzval))
-    get!(_bound, key) do
+    key = (_ensure_hash(A), x.structural_hash, T, Ti)
+    ops = get!(_bound, A) do
+        d = Dict{Any,BoundOp}()
+        finalizer(_ -> _release!(d), A)   # HPCSparseMatrix is a mutable struct (src/sparse.jl:319): it can carry a finalizer
+        d
+    end
+    get!(ops, key) do
         ctx = _context(A.backend)
         nnz = Int64(length(A.nzval))
         csr = Ref{Ptr{Cvoid}}(C_NULL)
@@ -86,21 +108,27 @@ function _bind(A::HPCSparseMatrix{T,Ti,B}, x::HPCVector{T}, plan::VectorPlan{T,T
                   Int64(A.ncols_compressed)::Int64, nnz::Int64, _dptr(A.rowptr_target)::Ptr{Cvoid}, _dptr(A.colval_target)::Ptr{Cvoid},
                   _dptr(A.nzval)::Ptr{Cvoid}, csr::Ptr{Ptr{Cvoid}})::Cint), "hpcla_csr_create")
         # hand over the VectorPlan the reference already built with MPI (src/sparse.jl:1875-1984): no second protocol
-        sidx = [pointer(v) for v in plan.send_indices]; slen = Int64[length(v) for v in plan.send_indices]
-        rprm = [pointer(v) for v in plan.recv_perm];    rlen = Int64[length(v) for v in plan.recv_perm]
+        # pointer tables as Vector{Ptr{Cvoid}} (the element type the C side declares: const void* const*), taken under
+        # GC.@preserve so that the index vectors cannot move or be collected while the library copies them
+        send_indices, recv_perm = plan.send_indices, plan.recv_perm
+        slen = Int64[length(v) for v in send_indices]
+        rlen = Int64[length(v) for v in recv_perm]
+        send_ids, recv_ids = Int64.(plan.send_rank_ids), Int64.(plan.recv_rank_ids)
         ph = Ref{Ptr{Cvoid}}(C_NULL)
-        GC.@preserve plan begin
+        GC.@preserve plan send_indices recv_perm send_ids recv_ids begin
+            sidx = Ptr{Cvoid}[Ptr{Cvoid}(pointer(v)) for v in send_indices]
+            rprm = Ptr{Cvoid}[Ptr{Cvoid}(pointer(v)) for v in recv_perm]
             _check(@ccall(libhpcla.hpcla_plan_import(comm_rank(A.backend.comm)::Cint, comm_size(A.backend.comm)::Cint, _itype(Ti)::Cint,
                       Int64(length(plan.gathered))::Int64, Int64(length(x.v))::Int64,
-                      Int64(length(plan.send_rank_ids))::Int64, Int64.(plan.send_rank_ids)::Ptr{Int64}, slen::Ptr{Int64}, sidx::Ptr{Ptr{Cvoid}},
-                      Int64(length(plan.recv_rank_ids))::Int64, Int64.(plan.recv_rank_ids)::Ptr{Int64}, rlen::Ptr{Int64}, rprm::Ptr{Ptr{Cvoid}},
+                      Int64(length(send_ids))::Int64, send_ids::Ptr{Int64}, slen::Ptr{Int64}, sidx::Ptr{Ptr{Cvoid}},
+                      Int64(length(recv_ids))::Int64, recv_ids::Ptr{Int64}, rlen::Ptr{Int64}, rprm::Ptr{Ptr{Cvoid}},
                       Int64(length(plan.local_src_indices))::Int64, plan.local_src_indices::Ptr{Cvoid}, plan.local_dst_indices::Ptr{Cvoid},
                       ph::Ptr{Ptr{Cvoid}})::Cint), "hpcla_plan_import")
         end
         op = Ref{Ptr{Cvoid}}(C_NULL)
         _check(@ccall(libhpcla.hpcla_spmv_create(ctx::Ptr{Cvoid}, csr[]::Ptr{Cvoid}, ph[]::Ptr{Cvoid}, Int64(length(x.v))::Int64,
                   op::Ptr{Ptr{Cvoid}})::Cint), "hpcla_spmv_create")
-        BoundOp(csr[], ph[], op[], (A.rowptr_target, A.colval_target, A.nzval))
+        BoundOp(csr[], ph[], op[], key)
     end
 end
 
@@ -270,12 +298,10 @@ end
 
 # --- cache hygiene: clear_plan_cache!() (src/HPCLinearAlgebra.jl:181-201) must also drop the device state ----------
 function clear_bound!()
-    for b in values(_bound)
-        @ccall libhpcla.hpcla_spmv_destroy(b.op::Ptr{Cvoid})::Cvoid
-        @ccall libhpcla.hpcla_plan_destroy(b.plan::Ptr{Cvoid})::Cvoid
-        @ccall libhpcla.hpcla_csr_destroy(b.csr::Ptr{Cvoid})::Cvoid
+    for ops in values(_bound)
+        _release!(ops)
     end
-    empty!(_bound)
+    return nothing
 end
 
 end # module

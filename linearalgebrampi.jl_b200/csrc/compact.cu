@@ -47,6 +47,7 @@ struct CWalkArgs {
     i64 nnz_total;
     TileRuns runs;
     int q0;  // position of this launch's first CTA in the compact list
+    int tail_q_min;  // first position in the compact list whose tile has tail elements of x (INT_MAX: none)
     int window, cw, chdr_bytes, chdr_fetch, cp_bytes, xcap;
     const T* dot_x;
     double* dot_out;
@@ -73,26 +74,25 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS) spmv_cwalk_kerne
     const i64 left = (a.nnz_total - w0) & ~(i64)3;
     const int n_fetch = (int)(left < (i64)a.cw ? (left > 0 ? left : 0) : (i64)a.cw);
     const unsigned char* ghdr = a.hdrs + q * (i64)a.chdr_bytes;
+    if (tid == 0) {
+        mbar_init(barA, 1);
+        mbar_init(barB, 1);
+        mbar_init(barX, 32);
+        mbar_fence_init();
+        const uint64_t pol = l2_evict_first_policy();
+        mbar_expect_tx(barA, (uint32_t)a.chdr_fetch + (uint32_t)a.cp_bytes);
+        bulk_g2s(const_cast<unsigned char*>(shdr), ghdr, (uint32_t)a.chdr_fetch, barA, pol);
+        bulk_g2s(const_cast<unsigned short*>(spos), a.colpos + q * (i64)a.cp_bytes, (uint32_t)a.cp_bytes, barA, pol);
+        mbar_expect_tx(barB, (uint32_t)n_fetch * (uint32_t)sizeof(T));
+        if (n_fetch > 0) bulk_g2s(sval, a.nzval + w0, (uint32_t)n_fetch * (uint32_t)sizeof(T), barB, pol);
+    }
+    __syncthreads();  // barriers initialised before anyone arrives or waits (nothing slow in front of this: no global load)
     if (tid < 32) {
-        uint64_t pol = 0;
-        if (tid == 0) {
-            mbar_init(barA, 1);
-            mbar_init(barB, 1);
-            mbar_init(barX, 32);
-            mbar_fence_init();
-            pol = l2_evict_first_policy();
-            mbar_expect_tx(barA, (uint32_t)a.chdr_fetch + (uint32_t)a.cp_bytes);
-            bulk_g2s(const_cast<unsigned char*>(shdr), ghdr, (uint32_t)a.chdr_fetch, barA, pol);
-            bulk_g2s(const_cast<unsigned short*>(spos), a.colpos + q * (i64)a.cp_bytes, (uint32_t)a.cp_bytes, barA, pol);
-            mbar_expect_tx(barB, (uint32_t)n_fetch * (uint32_t)sizeof(T));
-            if (n_fetch > 0) bulk_g2s(sval, a.nzval + w0, (uint32_t)n_fetch * (uint32_t)sizeof(T), barB, pol);
-        }
-        __syncwarp();
         // the x runs: lane j reads run j of the header straight from global memory (in parallel with the copies above)
         // and issues its bulk copy; x is re-read by the neighbouring tiles, so it keeps the default L2 policy
-        const int nruns = __ldg(reinterpret_cast<const int*>(ghdr) + 4);
+        // (unused table entries are zero: no second load that would depend on the run count)
         int4 run = make_int4(0, 0, 0, 0);
-        if (tid < CW_R && tid < nruns) run = __ldg(reinterpret_cast<const int4*>(ghdr + 32) + tid);
+        if (tid < CW_R) run = __ldg(reinterpret_cast<const int4*>(ghdr + 32) + tid);
         if (run.y > 0) {
             const uint32_t bytes = (uint32_t)run.y * (uint32_t)sizeof(T);
             mbar_expect_tx(barX, bytes);
@@ -102,26 +102,25 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS) spmv_cwalk_kerne
         } else {
             mbar_arrive(barX);
         }
-    } else if (tid < 64) {
-        // the <= 3 elements at the very end of x.v that no 16-byte copy may fetch (last tiles only)
-        const int tail_n = __ldg(reinterpret_cast<const int*>(ghdr) + 6);
-        if (tid - 32 < tail_n) {
-            const int tail_soff = __ldg(reinterpret_cast<const int*>(ghdr) + 7);
-            const int tail_xoff = __ldg(reinterpret_cast<const int*>(ghdr + 32) + 3);
-            sx[tail_soff + (tid - 32)] = a.x_own[tail_xoff + (tid - 32)];
-        }
     }
-    {  // the <= 3 values a 16-byte copy cannot fetch (end of A.nzval, last tile only)
-        const i64 avail = a.nnz_total - w0;
-        const int n_avail = (int)(avail < (i64)a.cw ? avail : (i64)a.cw);
-        for (int k = n_fetch + tid; k < n_avail; k += ROW_THREADS) sval[k] = a.nzval[w0 + k];
-    }
-    __syncthreads();  // barriers initialised (and the tails written) before anyone waits
     mbar_wait(barA, 0);
     const CHead* h = reinterpret_cast<const CHead*>(shdr);
     const i64 r0 = h->r0;
     const int nrows = h->nrows;
     const unsigned short* off = reinterpret_cast<const unsigned short*>(shdr + CW_HDR_FIXED);
+    {
+        // Rare and uniform per CTA: elements that no 16-byte copy may fetch — the <= 3 elements at the very end of x.v
+        // (only tiles from tail_q_min on can have them) and the <= 3 values at the end of A.nzval (last tile).
+        const i64 avail = a.nnz_total - w0;
+        const int n_avail = (int)(avail < (i64)a.cw ? avail : (i64)a.cw);
+        const bool x_tail = q >= (i64)a.tail_q_min, v_tail = n_fetch < n_avail;
+        if (x_tail || v_tail) {
+            if (x_tail && tid < h->tail_n) sx[h->tail_soff + tid] = a.x_own[reinterpret_cast<const CRun*>(shdr + 32)->tail_xoff + tid];
+            if (v_tail)
+                for (int k = n_fetch + tid; k < n_avail; k += ROW_THREADS) sval[k] = a.nzval[w0 + k];
+            __syncthreads();
+        }
+    }
     mbar_wait(barX, 0);
     mbar_wait(barB, 0);
     constexpr int RPP = ROW_THREADS / G;
@@ -180,7 +179,7 @@ template <class Ti, bool BUILD>
 __global__ void __launch_bounds__(256) compact_tile_kernel(const Ti* __restrict__ rowptr, const Ti* __restrict__ colval, const TileDesc* __restrict__ tiles,
                                                            const int* __restrict__ tile_ids, int window, i64 own_lo, i64 own_n, int elem_bytes,
                                                            CompactShape sh, int p2, int2* __restrict__ stats, unsigned char* __restrict__ hdrs,
-                                                           unsigned char* __restrict__ colpos) {
+                                                           unsigned char* __restrict__ colpos, int* __restrict__ tail_q_min) {
     extern __shared__ unsigned int keys[];  // [p2]
     __shared__ int run_xoff[CW_R + 1], run_len[CW_R + 1], run_soff[CW_R + 1];
     __shared__ int s_nruns, s_total, s_tail_n, s_tail_soff, s_tail_xoff;
@@ -260,6 +259,7 @@ __global__ void __launch_bounds__(256) compact_tile_kernel(const Ti* __restrict_
         hd->x_total = s_total;
         hd->tail_n = s_tail_n;
         hd->tail_soff = s_tail_soff;
+        if (s_tail_n > 0 && tail_q_min) atomicMin(tail_q_min, (int)blockIdx.x);
     }
     if (tid < CW_R) {
         CRun* rn = reinterpret_cast<CRun*>(h + 32) + tid;
@@ -308,13 +308,13 @@ static int pow2_at_least(int n) {
 
 cudaError_t launch_compact_tiles(bool build, int dtype, int itype, const void* rowptr, const void* colval, const TileDesc* tiles, const int* d_tile_ids, int n,
                                  int window, i64 own_lo, i64 own_n, const CompactShape& sh, int2* d_stats, unsigned char* d_hdrs, unsigned char* d_colpos,
-                                 cudaStream_t st) {
+                                 int* d_tail_q_min, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     const int p2 = pow2_at_least(sh.cw);
     if (p2 > 8192) return cudaErrorInvalidValue;
     const size_t smem = (size_t)p2 * 4;
     const int eb = dtype == HPCLA_F32 ? 4 : dtype == HPCLA_F64 ? 8 : 16;
-#define CT_LAUNCH(Ti, B) compact_tile_kernel<Ti, B><<<n, 256, smem, st>>>((const Ti*)rowptr, (const Ti*)colval, tiles, d_tile_ids, window, own_lo, own_n, eb, sh, p2, d_stats, d_hdrs, d_colpos)
+#define CT_LAUNCH(Ti, B) compact_tile_kernel<Ti, B><<<n, 256, smem, st>>>((const Ti*)rowptr, (const Ti*)colval, tiles, d_tile_ids, window, own_lo, own_n, eb, sh, p2, d_stats, d_hdrs, d_colpos, d_tail_q_min)
     if (itype == HPCLA_I32) {
         if (build) CT_LAUNCH(int, true);
         else CT_LAUNCH(int, false);
@@ -358,6 +358,7 @@ static cudaError_t cwalk_typed(const CWalkLaunch& L, cudaStream_t st) {
     a.nnz_total = L.nnz;
     a.runs = launch_runs(L.n_runs, L.run_cta0, L.run_tile0);
     a.q0 = L.q0;
+    a.tail_q_min = L.tail_q_min;
     a.window = L.window;
     a.cw = L.sh.cw;
     a.chdr_bytes = L.sh.chdr_bytes;

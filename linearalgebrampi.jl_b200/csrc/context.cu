@@ -114,6 +114,7 @@ struct hpcla_ctx {
     int device = 0, rank = 0, nranks = 1;
     cudaStream_t halo_stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;  // staged multiply (created on first use)
+    cudaStream_t cap_stream = nullptr;                        // graph capture (created on first use)
     ncclComm_t comm = nullptr;
     bool comm_owned = false;
     hpcla_group* group = nullptr;
@@ -121,6 +122,7 @@ struct hpcla_ctx {
     double* d_red_scratch = nullptr;  // reduce_scratch_doubles()
     double* d_red_out = nullptr;      // 8 doubles
     double* h_red_out = nullptr;      // pinned, 8 doubles
+    size_t l2_persist_max = 0, l2_window_max = 0, l2_persist_set = 0;  // persisting-L2 limits of the device / what has been set aside
 };
 
 struct hpcla_csr {
@@ -141,6 +143,7 @@ struct hpcla_csr {
     void* d_partials = nullptr;
     FlatData flat;        // irregular matrices: the nnz-split multiply (flat.cu); n_chunks == 0 otherwise
     bool flat_keep_x = false;  // gather x with an L2 evict-last hint (HPCLA_FLAT_KEEP_X)
+    bool flat_l2_window = true;  // pin the own segment of x in the persisting part of L2 during the launch (HPCLA_FLAT_L2_WINDOW=0: off)
 };
 
 struct Seg {
@@ -193,6 +196,7 @@ struct hpcla_spmv {
     // compact tiles (compact.cu): headers and 16-bit positions, by position in list [2][0]
     CompactShape csh{};
     unsigned char *d_chdr = nullptr, *d_cpos = nullptr;
+    int ctail_q_min = 0x7fffffff;
     struct HostPipe* pipe = nullptr;
     // fused dot(x, A x) for CG: one partial per row-walk CTA, interior list first, then boundary list
     double* d_dot_partials = nullptr;
@@ -278,6 +282,12 @@ extern "C" int hpcla_ctx_create(int device, int rank, int nranks, hpcla_ctx** ou
     CU_TRY(cudaMemset(c->d_red_scratch, 0, sizeof(double) * reduce_scratch_doubles()));
     CU_TRY(cudaMalloc(&c->d_red_out, sizeof(double) * 8));
     CU_TRY(cudaMallocHost(&c->h_red_out, sizeof(double) * 8));
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, device) == cudaSuccess) c->l2_persist_max = (size_t)v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, device) == cudaSuccess) c->l2_window_max = (size_t)v;
+        cudaGetLastError();
+    }
     *out = c;
     return HPCLA_OK;
 }
@@ -435,6 +445,7 @@ extern "C" void hpcla_ctx_destroy(hpcla_ctx* ctx) {
     if (ctx->halo_stream) cudaStreamDestroy(ctx->halo_stream);
     if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     cudaFree(ctx->d_red_scratch);
     cudaFree(ctx->d_red_out);
     cudaFreeHost(ctx->h_red_out);
@@ -587,6 +598,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         CU_TRY(flat_build(itype, d_rowptr, nrows, nnz, &A->flat, st));
         CU_TRY(cudaMalloc(&A->flat.d_heads, dtype_size(dtype) * (size_t)std::max<i64>(A->flat.n_wchunks, 1)));
         if (const char* e = getenv("HPCLA_FLAT_KEEP_X")) A->flat_keep_x = e[0] == '1';
+        if (const char* e = getenv("HPCLA_FLAT_L2_WINDOW")) A->flat_l2_window = e[0] != '0';
     }
     // rows longer than the split threshold (rare: power-law tails)
     const i64 cap = nnz / A->long_threshold + 1;
@@ -671,6 +683,15 @@ static int build_compact(hpcla_spmv* op, std::vector<int> (&lists)[3][2]) {
     const hpcla_csr* A = op->csr;
     const char* env = getenv("HPCLA_COMPACT");
     if (env && env[0] == '0') return HPCLA_OK;
+    if (!(env && env[0] == '1')) {
+        // Default: where it pays.  The compact walk trades the column indices for 16-bit positions and a longer start-up
+        // chain per tile (header -> x runs); it wins when the multiply is bound by DRAM traffic and the indices are a fair
+        // share of it.  Matrices that fit L2 (latency-bound: the direct walk has no dependent load at all) and element
+        // types whose values dwarf the indices (ComplexF64 with Int32: 2 of 20 bytes) keep the plain / direct walk.
+        const double per_nz = (double)(dtype_size(A->dtype) + itype_size(A->itype));
+        const double saving = ((double)itype_size(A->itype) - 2.0) / per_nz;
+        if (saving < 0.15 || (double)A->nnz * per_nz < 96.0e6) return HPCLA_OK;
+    }
     if (A->shape.lanes <= 0 || !op->x_in_place || op->own_n >= (i64)INT32_MAX || lists[0][0].empty()) return HPCLA_OK;
     CompactShape sh = compact_shape(A->dtype, A->shape);
     if (sh.cw <= 0 || sh.cw > 8192) return HPCLA_OK;
@@ -687,7 +708,7 @@ static int build_compact(hpcla_spmv* op, std::vector<int> (&lists)[3][2]) {
     } free2{d_ids, d_stats};
     CU_TRY(cudaMemcpyAsync(d_ids, lists[0][0].data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, st));
     CU_TRY(launch_compact_tiles(false, A->dtype, A->itype, A->d_rowptr, A->d_colval, A->d_tiles, d_ids, n, A->shape.window, op->own_lo, op->own_n, sh, d_stats,
-                                nullptr, nullptr, st));
+                                nullptr, nullptr, nullptr, st));
     std::vector<int2> stats((size_t)n);
     CU_TRY(cudaMemcpyAsync(stats.data(), d_stats, sizeof(int2) * (size_t)n, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -705,8 +726,12 @@ static int build_compact(hpcla_spmv* op, std::vector<int> (&lists)[3][2]) {
     CU_TRY(cudaMalloc(&op->d_chdr, (size_t)nc * (size_t)sh.chdr_bytes));
     CU_TRY(cudaMalloc(&op->d_cpos, (size_t)nc * (size_t)sh.cp_bytes));
     CU_TRY(cudaMemsetAsync(op->d_chdr, 0, (size_t)nc * (size_t)sh.chdr_bytes, st));
+    int* d_tail = reinterpret_cast<int*>(d_stats);  // (the stats are no longer needed)
+    op->ctail_q_min = 0x7fffffff;
+    CU_TRY(cudaMemcpyAsync(d_tail, &op->ctail_q_min, sizeof(int), cudaMemcpyHostToDevice, st));
     CU_TRY(launch_compact_tiles(true, A->dtype, A->itype, A->d_rowptr, A->d_colval, A->d_tiles, d_ids, nc, A->shape.window, op->own_lo, op->own_n, sh, nullptr,
-                                op->d_chdr, op->d_cpos, st));
+                                op->d_chdr, op->d_cpos, d_tail, st));
+    CU_TRY(cudaMemcpyAsync(&op->ctail_q_min, d_tail, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     op->csh = sh;
     lists[2][0].swap(chosen);
@@ -1060,6 +1085,7 @@ static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t s
             C.hdrs = op->d_chdr;
             C.colpos = op->d_cpos;
             C.q0 = lo;
+            C.tail_q_min = op->ctail_q_min;
             C.n_runs = L.n_runs;
             for (int j = 0; j < 9; ++j) C.run_cta0[j] = L.run_cta0[j];
             for (int j = 0; j < 8; ++j) C.run_tile0[j] = L.run_tile0[j];
@@ -1095,7 +1121,35 @@ static int launch_flat(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stre
     F.keep_x = A->flat_keep_x;
     F.y = base.y;
     F.long_threshold = A->long_threshold;
-    CU_TRY(launch_spmv_flat(F, stream));
+    // x is the one array this multiply re-reads (every stored entry gathers from it) while 40x as many bytes of matrix
+    // stream through L2: when the own segment of x fits, it is pinned in the persisting part of L2 for the duration of the
+    // launch (access-policy window on the stream; HPCLA_FLAT_L2_WINDOW=0 disables).
+    bool window = false;
+    const size_t xbytes = (size_t)op->own_n * dtype_size(A->dtype);
+    if (A->flat_l2_window && base.x_own && xbytes > 0 && xbytes <= op->ctx->l2_persist_max) {
+        hpcla_ctx* ctx = op->ctx;
+        if (ctx->l2_persist_set < xbytes) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min(ctx->l2_persist_max, xbytes + (xbytes >> 3))) == cudaSuccess) ctx->l2_persist_set = xbytes;
+            else cudaGetLastError();
+        }
+        if (ctx->l2_persist_set >= xbytes) {
+            cudaStreamAttrValue attr{};
+            attr.accessPolicyWindow.base_ptr = const_cast<void*>(base.x_own);
+            attr.accessPolicyWindow.num_bytes = std::min(xbytes, ctx->l2_window_max);
+            attr.accessPolicyWindow.hitRatio = 1.0f;
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess) window = true;
+            else cudaGetLastError();
+        }
+    }
+    const cudaError_t le = launch_spmv_flat(F, stream);
+    if (window) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
+    CU_TRY(le);
     op->launches += 2 + (A->flat.n_empty > 0 ? 1 : 0);
     return HPCLA_OK;
 }
@@ -1268,7 +1322,10 @@ extern "C" int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: the previous call was not finished");
     int rc = set_device(op->ctx);
     if (rc) return rc;
-    cudaStream_t stream = (cudaStream_t)stream_;
+    (void)stream_;  // the capture runs on a library-owned stream: the caller's may be the legacy default stream, which cannot be captured
+    hpcla_ctx* ctx = op->ctx;
+    if (!ctx->cap_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t stream = ctx->cap_stream;
     if (op->graph) {
         cudaGraphExecDestroy(op->graph);
         op->graph = nullptr;
@@ -1833,18 +1890,21 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
         op->launches += op->cg_graph_launches;
     } else {
         const i64 before = op->launches;
+        cudaStream_t es = stream;  // the stream the loop is enqueued on: the caller's, or the library's capture stream
         if (want_graph) {
             if (op->cg_graph) cudaGraphExecDestroy(op->cg_graph);
             op->cg_graph = nullptr;
-            CU_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeRelaxed));
+            if (!ctx->cap_stream) CU_TRY(cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+            es = ctx->cap_stream;
+            CU_TRY(cudaStreamBeginCapture(es, cudaStreamCaptureModeRelaxed));
         }
         const bool tl = op->timeline;
         if (want_graph) op->timeline = false;
-        rc = cg_enqueue(op, d_b, d_x, r, p, q, iters, fused, n_partials, d_s, d_pq, stream);
+        rc = cg_enqueue(op, d_b, d_x, r, p, q, iters, fused, n_partials, d_s, d_pq, es);
         op->timeline = tl;
         if (want_graph) {
             cudaGraph_t g = nullptr;
-            cudaError_t ce = cudaStreamEndCapture(stream, &g);
+            cudaError_t ce = cudaStreamEndCapture(es, &g);
             op->phase = 0;
             if (rc || ce != cudaSuccess || !g) {
                 if (g) cudaGraphDestroy(g);

@@ -129,7 +129,7 @@ size_t cwalk_smem_bytes(int dtype, const CompactShape& sh);
 // one CTA per listed tile: build == false: stats[i] = {x runs or -1, staged x elements}; build == true: headers + positions
 cudaError_t launch_compact_tiles(bool build, int dtype, int itype, const void* rowptr, const void* colval, const TileDesc* tiles, const int* d_tile_ids, int n,
                                  int window, i64 own_lo, i64 own_n, const CompactShape& sh, int2* d_stats, unsigned char* d_hdrs, unsigned char* d_colpos,
-                                 cudaStream_t st);
+                                 int* d_tail_q_min, cudaStream_t st);
 struct CWalkLaunch {
     int dtype, lanes, window;
     const void* nzval;
@@ -138,6 +138,7 @@ struct CWalkLaunch {
     const unsigned char* hdrs;
     const unsigned char* colpos;
     int q0;  // position of the first CTA's tile in the compact list
+    int tail_q_min = 0x7fffffff;  // first position whose tile has tail elements of x
     int n_runs = 0;
     int run_cta0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int run_tile0[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -106,113 +106,155 @@ __device__ __forceinline__ T flat_x(const XView<T>& xv, Ti c, uint64_t pol) {
     return ld_x(p + (i64)c);
 }
 
-template <class T> struct FlatCfg { static constexpr int AHEAD = 4, CTAS = 4; };   // rounds of gathers issued before the first product
-template <> struct FlatCfg<float> { static constexpr int AHEAD = 4, CTAS = 5; };
-template <> struct FlatCfg<cplx> { static constexpr int AHEAD = 1, CTAS = 2; };
+// Warps per CTA (one persistent CTA per SM).  What bounds this kernel is the number of scattered x gathers an SM keeps
+// in flight, and those live in the L1 lines that the shared-memory carve-out leaves over (measured, tools/gather_probe.cu
+// and profiles/r2a_*, r2b_*: 0.87 gathers per clock and SM with ~190 KB of L1, a third of that with 60 KB).  So the
+// kernel stages as little as it can: every warp keeps a two-stage ring holding only the COLUMN INDICES and row-start flags
+// of its 512-entry warp chunks (they are needed a whole chunk ahead, to issue the gathers); the values are fetched with
+// 128-bit streaming loads straight into registers, one chunk ahead as well.  As many warps as fit in ~60 KB.
+template <class T, class Ti> struct FlatCfg {
+    static constexpr int STAGE = 64 + FLAT_WCHUNK * (int)sizeof(Ti);
+    static constexpr int FIT = (60 * 1024) / (2 * STAGE);
+    static constexpr int BY_REGS = sizeof(T) <= 4 ? 16 : sizeof(T) <= 8 ? 12 : 6;  // x and values of two chunks live in registers
+    static constexpr int WARPS = FIT < BY_REGS ? FIT : BY_REGS;
+    static constexpr bool PREFETCH = sizeof(T) <= 8;  // gathers and values of the next chunk in flight while this one is reduced
+};
+
+// 4 consecutive values from a 16-byte aligned global address, streaming (each value is used once)
+__device__ __forceinline__ void ldg4_stream(const float* p, float (&v)[4]) { ld4_stream(p, v); }
+__device__ __forceinline__ void ldg4_stream(const double* p, double (&v)[4]) { ld4_stream(p, v); }
+__device__ __forceinline__ void ldg4_stream(const cplx* p, cplx (&v)[4]) { ld4_stream(p, v); }
 
 template <class T, class Ti, bool GHOST, bool KEEP>
-__global__ void __launch_bounds__(FLAT_THREADS, FlatCfg<T>::CTAS) spmv_flat_kernel(const FlatArgs<T, Ti> a) {
+__global__ void __launch_bounds__(FlatCfg<T, Ti>::WARPS * 32, 1) spmv_flat_kernel(const FlatArgs<T, Ti> a, i64 n_wchunks) {
+    using Cfg = FlatCfg<T, Ti>;
+    constexpr int WARPS = Cfg::WARPS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    unsigned* sbits = reinterpret_cast<unsigned*>(smem_raw + 16);
-    Ti* scol = reinterpret_cast<Ti*>(smem_raw + 16 + FLAT_WORDS * 4);
-    T* sval = reinterpret_cast<T*>(scol + FLAT_CHUNK);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const i64 chunk = blockIdx.x;
-    const i64 k0 = chunk * FLAT_CHUNK;
-    const i64 left = a.nnz - k0;
-    const int n_have = (int)(left < FLAT_CHUNK ? left : FLAT_CHUNK);  // > 0
-    const int n_bulk = n_have & ~3;
-    if (tid == 0) {
-        mbar_init(bar, 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;  // this warp's two barriers
+    unsigned char* ring = smem_raw + 256 + (size_t)warp * 2 * Cfg::STAGE;
+    const i64 total_warps = (i64)gridDim.x * WARPS;
+    i64 wc = (i64)blockIdx.x * WARPS + warp;  // this warp takes chunks wc, wc + total_warps, ...
+    if (wc >= n_wchunks) return;              // (warps are independent: no CTA-wide synchronisation anywhere)
+    uint64_t pol = 0, xpol = 0;
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
         mbar_fence_init();
-        const uint64_t pol = l2_evict_first_policy();
-        mbar_expect_tx(bar, (uint32_t)(FLAT_WORDS * 4) + (uint32_t)n_bulk * (uint32_t)(sizeof(Ti) + sizeof(T)));
-        bulk_g2s(sbits, a.bits + chunk * FLAT_WORDS, FLAT_WORDS * 4, bar, pol);
-        if (n_bulk > 0) {
-            bulk_g2s(scol, a.colval + k0, (uint32_t)n_bulk * (uint32_t)sizeof(Ti), bar, pol);
-            bulk_g2s(sval, a.nzval + k0, (uint32_t)n_bulk * (uint32_t)sizeof(T), bar, pol);
-        }
+        pol = l2_evict_first_policy();
     }
-    for (int k = n_bulk + tid; k < n_have; k += FLAT_THREADS) {  // the <= 3 entries a 16-byte copy cannot fetch (end of the arrays)
-        scol[k] = a.colval[k0 + k];
-        sval[k] = a.nzval[k0 + k];
-    }
-    __syncthreads();  // barrier initialised (and the tail written) before anyone waits
-    mbar_wait(bar, 0);
-
-    const int base = warp * FLAT_WCHUNK;
-    if (base >= n_have) return;  // (no CTA-wide synchronisation below)
-    const i64 wc = chunk * (FLAT_THREADS / 32) + warp;
-    uint64_t xpol = 0;
     if (KEEP) xpol = l2_evict_last_policy();
-    constexpr int AHEAD = FlatCfg<T>::AHEAD;
+    __syncwarp();
     const unsigned lt = (1u << lane) - 1u;
-    const int first_flag = (int)(sbits[warp * (FLAT_WCHUNK / 32)] & 1u);
-    i64 ord_open = __ldg(a.wrow + wc) - first_flag;  // ordinal of the row that is open in front of this round's first entry
-    T carry = el_zero(T());                          // its partial sum so far (within this warp chunk)
-    bool chunk_seen = false;                         // a row start has been met in this warp chunk
-    auto row_of = [&](i64 ord) -> i64 { return a.row_map ? __ldg(a.row_map + ord) : ord; };
-
+    auto stage_bits = [&](int s) { return reinterpret_cast<unsigned*>(ring + (size_t)s * Cfg::STAGE); };
+    auto stage_col = [&](int s) { return reinterpret_cast<Ti*>(ring + (size_t)s * Cfg::STAGE + 64); };
+    auto have = [&](i64 c) { const i64 left = a.nnz - c * FLAT_WCHUNK; return (int)(left < FLAT_WCHUNK ? left : FLAT_WCHUNK); };
+    // fetch the row-start flags and column indices of warp chunk c into stage s: two bulk copies on the stage's barrier
+    auto issue = [&](i64 c, int s) {
+        const int n_have = have(c), n_bulk = n_have & ~3;
+        const i64 k0 = c * FLAT_WCHUNK;
+        if (lane == 0) {
+            mbar_expect_tx(bars + s, 64u + (uint32_t)n_bulk * (uint32_t)sizeof(Ti));
+            bulk_g2s(stage_bits(s), a.bits + c * (FLAT_WCHUNK / 32), 64, bars + s, pol);
+            if (n_bulk > 0) bulk_g2s(stage_col(s), a.colval + k0, (uint32_t)n_bulk * (uint32_t)sizeof(Ti), bars + s, pol);
+        }
+        if (lane < n_have - n_bulk) stage_col(s)[n_bulk + lane] = a.colval[k0 + n_bulk + lane];  // (end of the arrays)
+    };
+    // all 16 gathers of a lane go out together, and the 16 values behind them
+    auto gather = [&](i64 c, int s, T (&xg)[FLAT_ROUNDS][4], T (&vg)[FLAT_ROUNDS][4]) {
+        const int n_have = have(c);
+        const Ti* scol = stage_col(s);
+        const T* gval = a.nzval + c * FLAT_WCHUNK;
 #pragma unroll
-    for (int jb = 0; jb < FLAT_ROUNDS; jb += AHEAD) {
-        T xg[AHEAD][4];
-#pragma unroll
-        for (int jj = 0; jj < AHEAD; ++jj) {  // all gathers of AHEAD rounds go out before the first product
-            const int e = base + 128 * (jb + jj) + 4 * lane;
-            Ti c[4];
-            lds4(scol + e, c);
+        for (int j = 0; j < FLAT_ROUNDS; ++j) {
+            const int e = 128 * j + 4 * lane;
+            Ti cc[4];
+            lds4(scol + e, cc);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const Ti col = (e + k < n_have) ? c[k] : (Ti)a.safe_col;
-                xg[jj][k] = flat_x<GHOST, KEEP, T, Ti>(a.xv, col, xpol);
+                const Ti col = (e + k < n_have) ? cc[k] : (Ti)a.safe_col;
+                xg[j][k] = flat_x<GHOST, KEEP, T, Ti>(a.xv, col, xpol);
             }
         }
 #pragma unroll
-        for (int jj = 0; jj < AHEAD; ++jj) {
-            const int j = jb + jj;
-            const int e = base + 128 * j + 4 * lane;
-            T v[4], p[4];
-            lds4(sval + e, v);
+        for (int j = 0; j < FLAT_ROUNDS; ++j) {
+            const int e = 128 * j + 4 * lane;
+            if (e + 4 <= n_have) {
+                ldg4_stream(gval + e, vg[j]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) p[k] = (e + k < n_have) ? el_mul(v[k], xg[jj][k]) : el_zero(T());
-            const unsigned f = (sbits[warp * (FLAT_WCHUNK / 32) + 4 * j + (lane >> 3)] >> (4 * (lane & 7))) & 0xFu;
+                for (int k = 0; k < 4; ++k) vg[j][k] = (e + k < n_have) ? ld_stream(gval + e + k) : el_zero(T());
+            }
+        }
+    };
+    auto row_of = [&](i64 ord) -> i64 { return a.row_map ? __ldg(a.row_map + ord) : ord; };
+    // reduce warp chunk c (flags staged in s, x and values in registers) by row: register-level segmented scan, 4 rounds of
+    // 128 entries.  The lane boundaries of the scan come from one ballot (no flag shuffles); the common case of at most one
+    // row start among a lane's 4 entries is branch-free.
+    auto reduce = [&](i64 c, int s, const T (&xg)[FLAT_ROUNDS][4], const T (&vg)[FLAT_ROUNDS][4], i64 wrow_c) {
+        const int n_have = have(c);
+        const unsigned* sbits = stage_bits(s);
+        const int first_flag = (int)(sbits[0] & 1u);
+        i64 ord_open = wrow_c - first_flag;  // ordinal of the row that is open in front of this round's first entry
+        T carry = el_zero(T());              // its partial sum so far (within this warp chunk)
+        bool chunk_seen = false;             // a row start has been met in this warp chunk
+#pragma unroll
+        for (int j = 0; j < FLAT_ROUNDS; ++j) {
+            const int e = 128 * j + 4 * lane;
+            T p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p[k] = (e + k < n_have) ? el_mul(vg[j][k], xg[j][k]) : el_zero(T());
+            const unsigned f = (e < n_have) ? (sbits[4 * j + (lane >> 3)] >> (4 * (lane & 7))) & 0xFu : 0u;
+            const int nf = __popc(f);
             // row starts in front of my entries in this round, and in the whole round
             const unsigned b0 = __ballot_sync(0xffffffffu, f & 1u), b1 = __ballot_sync(0xffffffffu, f & 2u);
             const unsigned b2 = __ballot_sync(0xffffffffu, f & 4u), b3 = __ballot_sync(0xffffffffu, f & 8u);
             const int nbefore = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
             const int ntotal = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-            // my 4 entries: head = what belongs to the row open in front of me, tail = what my last row start has so far;
-            // rows that start and end inside my 4 entries are complete
-            T acc = el_zero(T()), head = el_zero(T());
-            bool seen = false;
-            i64 cur = ord_open + nbefore;
+            // my 4 entries: head = what belongs to the row open in front of me, tail = what my last row start has so far
+            T head, tail;
+            const bool seen = nf > 0;
+            if (__any_sync(0xffffffffu, nf > 1)) {  // rare (rows shorter than 4 entries): rows that start AND end inside my 4 entries
+                T acc = el_zero(T());
+                head = el_zero(T());
+                bool sn = false;
+                i64 cur = ord_open + nbefore;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if ((f >> k) & 1u) {
-                    if (!seen) head = acc, seen = true;
-                    else st_y(a.y + row_of(cur), acc);
-                    cur += 1;
-                    acc = p[k];
-                } else {
-                    acc = el_add(acc, p[k]);
+                for (int k = 0; k < 4; ++k) {
+                    if ((f >> k) & 1u) {
+                        if (!sn) head = acc, sn = true;
+                        else st_y(a.y + row_of(cur), acc);
+                        cur += 1;
+                        acc = p[k];
+                    } else {
+                        acc = el_add(acc, p[k]);
+                    }
                 }
+                if (!sn) head = acc;
+                tail = acc;
+            } else {
+                const int pos = seen ? __ffs((int)f) - 1 : 4;  // my (only) row start
+                head = el_zero(T());
+                tail = el_zero(T());
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    head = el_add(head, k < pos ? p[k] : el_zero(T()));
+                    tail = el_add(tail, k >= pos ? p[k] : el_zero(T()));
+                }
+                if (!seen) tail = head;
             }
-            if (!seen) head = acc;
             // segmented inclusive scan of the tails over the lanes (a lane with a row start begins a new segment)
-            T sv = acc;
-            bool fl = seen;
+            const unsigned seen_mask = __ballot_sync(0xffffffffu, seen);
+            const unsigned below = seen_mask & (lt | (1u << lane));     // lanes with a row start, up to and including me
+            const int seg_lo = below ? 31 - __clz((int)below) : 0;     // first lane of my segment
+            T sv = tail;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const T vu = shfl_up(sv, d);
-                const bool fu = __shfl_up_sync(0xffffffffu, (int)fl, d) != 0;
-                if (lane >= d) {
-                    if (!fl) sv = el_add(vu, sv);
-                    fl = fl || fu;
-                }
+                if (lane - d >= seg_lo) sv = el_add(vu, sv);
             }
             const T pv = shfl_up(sv, 1);
-            const bool pf = __shfl_up_sync(0xffffffffu, (int)fl, 1) != 0;
+            const bool pf = (seen_mask & lt) != 0u;
             T cin = carry;
             bool before_seen = chunk_seen;
             if (lane > 0) {
@@ -222,18 +264,53 @@ __global__ void __launch_bounds__(FLAT_THREADS, FlatCfg<T>::CTAS) spmv_flat_kern
             if (seen) {  // the row open in front of me ends at my first row start
                 const T total = el_add(cin, head);
                 if (before_seen) st_y(a.y + row_of(ord_open + nbefore), total);
-                else a.heads[wc] = total;  // it began before this warp chunk (0 if the chunk begins with a row start)
+                else a.heads[c] = total;  // it began before this warp chunk (0 if the chunk begins with a row start)
             }
             const T lastv = shfl_idx(sv, 31);
-            const bool lastf = __shfl_sync(0xffffffffu, (int)fl, 31) != 0;
+            const bool lastf = seen_mask != 0u;
             carry = lastf ? lastv : el_add(carry, lastv);
             chunk_seen = chunk_seen || lastf;
             ord_open += ntotal;
         }
-    }
-    if (lane == 0) {  // the row still open at the end of the warp chunk
-        if (chunk_seen) st_y(a.y + row_of(ord_open), carry);  // it began here: its first part; the following heads are added by the fix-up
-        else a.heads[wc] = carry;                             // the whole warp chunk lies inside one row
+        if (lane == 0) {  // the row still open at the end of the warp chunk
+            if (chunk_seen) st_y(a.y + row_of(ord_open), carry);  // it began here: its first part; the following heads are added by the fix-up
+            else a.heads[c] = carry;                              // the whole warp chunk lies inside one row
+        }
+    };
+
+    // software pipeline per warp: copy of chunk i+2 | gathers + values of chunk i+1 | reduction of chunk i
+    uint32_t ph0 = 0, ph1 = 0;  // phase parity to wait for, per stage
+    issue(wc, 0);
+    if (wc + total_warps < n_wchunks) issue(wc + total_warps, 1);
+    __syncwarp();
+    T xa[FLAT_ROUNDS][4], va[FLAT_ROUNDS][4], xb[FLAT_ROUNDS][4], vb[FLAT_ROUNDS][4];
+    i64 wrow_a = __ldg(a.wrow + wc), wrow_b = 0;
+    mbar_wait(bars, ph0);
+    ph0 ^= 1;
+    if (Cfg::PREFETCH) gather(wc, 0, xa, va);
+    int s = 0;
+    for (; wc < n_wchunks; wc += total_warps) {
+        __syncwarp();  // (the tail entries a lane may have written into a stage are visible to the others)
+        const i64 nxt = wc + total_warps;
+        const bool more = nxt < n_wchunks;
+        if (more) {
+            wrow_b = __ldg(a.wrow + nxt);
+            if (s == 0) mbar_wait(bars + 1, ph1), ph1 ^= 1;
+            else mbar_wait(bars, ph0), ph0 ^= 1;
+            if (Cfg::PREFETCH) gather(nxt, s ^ 1, xb, vb);
+        }
+        if (!Cfg::PREFETCH) gather(wc, s, xa, va);
+        reduce(wc, s, xa, va, wrow_a);
+        __syncwarp();  // every lane is done with stage s before it is refilled
+        if (nxt + total_warps < n_wchunks) issue(nxt + total_warps, s);
+        if (Cfg::PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < FLAT_ROUNDS; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xa[j][k] = xb[j][k], va[j][k] = vb[j][k];
+        }
+        wrow_a = wrow_b;
+        s ^= 1;
     }
 }
 
@@ -369,25 +446,49 @@ void flat_free(FlatData* F) {
     *F = FlatData{};
 }
 
-size_t flat_smem_bytes(int dtype, int itype) {
-    const size_t ts = dtype == HPCLA_F32 ? 4 : dtype == HPCLA_F64 ? 8 : 16, is = itype == HPCLA_I32 ? 4 : 8;
-    return 16 + (size_t)FLAT_WORDS * 4 + (size_t)FLAT_CHUNK * (is + ts);
-}
+template <class T, class Ti>
+static size_t flat_smem() { return 256 + (size_t)FlatCfg<T, Ti>::WARPS * 2 * FlatCfg<T, Ti>::STAGE; }
 int flat_max_run(i64 long_threshold) { return (int)(long_threshold / FLAT_WCHUNK) + 3; }
+
+// opt-in dynamic shared memory and a carve-out that leaves the rest of the SM's 228 KB to L1 (the gathers' lines)
+template <auto Kernel>
+static cudaError_t flat_configure(size_t smem) {
+    static bool done[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev & 63]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int pct = (int)((smem + 1024) * 100 / (228 * 1024)) + 1;  // the driver rounds up to the next carve-out it supports
+    e = cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e != cudaSuccess) return e;
+    done[dev & 63] = true;
+    return cudaSuccess;
+}
 
 template <class T, class Ti, bool GHOST, bool KEEP>
 static cudaError_t flat_launch_one(const FlatLaunch& L, const FlatArgs<T, Ti>& a, cudaStream_t st) {
-    const size_t smem = flat_smem_bytes(L.dtype, L.itype);
+    const size_t smem = flat_smem<T, Ti>();
     cudaError_t e;
-    if ((e = ensure_smem<spmv_flat_kernel<T, Ti, GHOST, KEEP>>(smem, false)) != cudaSuccess) return e;
-    spmv_flat_kernel<T, Ti, GHOST, KEEP><<<(unsigned)L.flat->n_chunks, FLAT_THREADS, smem, st>>>(a);
+    if ((e = flat_configure<spmv_flat_kernel<T, Ti, GHOST, KEEP>>(smem)) != cudaSuccess) return e;
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!sms[dev & 63]) cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    constexpr int WARPS = FlatCfg<T, Ti>::WARPS;
+    i64 grid = sms[dev & 63] > 0 ? sms[dev & 63] : 148;  // one persistent CTA per SM
+    const i64 need = (L.flat->n_wchunks + WARPS - 1) / WARPS;
+    if (grid > need) grid = need;
+    spmv_flat_kernel<T, Ti, GHOST, KEEP><<<(unsigned)grid, WARPS * 32, smem, st>>>(a, L.flat->n_wchunks);
     return cudaGetLastError();
 }
 
 template <class T, class Ti>
 static cudaError_t flat_typed(const FlatLaunch& L, cudaStream_t st) {
     const FlatData& F = *L.flat;
-    if (F.n_chunks == 0) return cudaSuccess;
+    if (F.n_wchunks == 0) return cudaSuccess;
     FlatArgs<T, Ti> a;
     a.colval = (const Ti*)L.colval;
     a.nzval = (const T*)L.nzval;
