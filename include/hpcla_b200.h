@@ -185,6 +185,16 @@ int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x, void* d_y,
  * (strong scaling: tens of microseconds of kernel per step against ~10 driver calls). */
 int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d_y, void* stream);
 int hpcla_spmv_graph_launch(hpcla_spmv* op, void* stream);
+/* Direct halo (optional; grouped ncclSend/ncclRecv stays the default): the ghost runs are PUSHED into the neighbours'
+ * `gathered` buffers over NVLink by the copy engine and announced with flags that the receiving halo stream waits on with
+ * stream memory operations — no NCCL kernel, no rendezvous, no kernel that spins.  Replaces the same Isend/Irecv/Waitall of
+ * src/vectors.jl:431-457.  Collective set-up through the host, like the 128-byte NCCL id (ext:411-443): every rank exports
+ * a blob (CUDA IPC handles of its `gathered` and flag buffers + where each neighbour's run lands), the host communicator
+ * all-gathers the blobs in rank order, every rank connects.  Works between processes (IPC) and between the rank-threads
+ * of one process (plain pointers).  Afterwards hpcla_spmv_run / begin+finish / gather / run_staged / hpcla_cg use it. */
+int hpcla_spmv_halo_blob_size(const hpcla_spmv* op, int64_t* bytes_out);
+int hpcla_spmv_halo_export(hpcla_spmv* op, void* blob_out);
+int hpcla_spmv_halo_connect(hpcla_spmv* op, const void* blobs /* nranks blobs, rank order */);
 /* Timeline of the most recent multiply, for operators created with HPCLA_TIMELINE=1 in the environment: milliseconds
  * from "x ready on the caller's stream" to the end of [0] the halo exchange, [1] the boundary tiles (both on the halo
  * stream), [2] the interior tiles, [3] the whole call (caller's stream); -1 where a step does not exist.  Blocks. */

@@ -16,7 +16,7 @@ from .vectors import (  # noqa: F401
     HPCVector, VectorRepartitionPlan, axpby, compute_partition_hash, dot, get_repartition_plan, norm, repartition, uniform_partition,
 )
 from .sparse import (  # noqa: F401
-    HPCSparseMatrix, Transpose, VectorPlan, build_vector_plan, cache_sizes, cg, clear_plan_cache, compute_structural_hash,
+    HPCSparseMatrix, Transpose, VectorPlan, build_vector_plan, cache_sizes, cg, clear_plan_cache, compute_structural_hash, enable_direct_halo,
     execute_plan, get_vector_plan, host_buffer, materialize_transpose, matvec, mul, mul_graph, mul_staged, spmv_info, spmv_timeline, to_backend, transpose, transpose_matvec,
     vec_adjoint_mul, vec_transpose_mul,
 )

@@ -86,6 +86,9 @@ SIGNATURES = {
     "hpcla_spmv_graph_capture": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_graph_launch": (_i, [_vp, _vp]),
     "hpcla_spmv_timeline": (_i, [_vp, _vp]),
+    "hpcla_spmv_halo_blob_size": (_i, [_vp, _vp]),
+    "hpcla_spmv_halo_export": (_i, [_vp, _vp]),
+    "hpcla_spmv_halo_connect": (_i, [_vp, _vp]),
     "hpcla_spmv_begin": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_finish": (_i, [_vp]),
     "hpcla_spmm_run": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),

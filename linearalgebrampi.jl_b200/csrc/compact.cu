@@ -121,17 +121,23 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS) spmv_cwalk_kerne
             __syncthreads();
         }
     }
-    mbar_wait(barX, 0);
-    mbar_wait(barB, 0);
     constexpr int RPP = ROW_THREADS / G;
     constexpr int B = HPCLA_WALK_BATCH;
     const int lane = tid % G;
     double dot = 0.0;
+    // fused dot (CG's p.q): this thread's element of p for its first row is requested now, so that the load flies while the
+    // x runs and the values are still landing (it is the only global load of the walk)
+    T dx0 = el_zero(T());
+    if (DOT && lane == 0 && tid / G < nrows) dx0 = ld_x(a.dot_x + r0 + tid / G);
+    mbar_wait(barX, 0);
+    mbar_wait(barB, 0);
     for (int base = 0; base < nrows; base += RPP) {
         const int i = base + tid / G;
         const bool valid = i < nrows;
         const int b = valid ? (int)off[i] : 0;
         const int e = valid ? (int)off[i + 1] : 0;
+        T dx = dx0;
+        if (DOT && base > 0 && valid && lane == 0) dx = ld_x(a.dot_x + r0 + i);
         T acc = el_zero(T());
         for (int k = b + lane; k < e; k += B * G) {
             T p[B];
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS) spmv_cwalk_kerne
         }
         if (valid && lane == 0) {
             st_y(a.y + r0 + i, acc);
-            if (DOT) dot += dot_term(ld_x(a.dot_x + r0 + i), acc);
+            if (DOT) dot += dot_term(dx, acc);
         }
     }
     if (DOT) {  // CG's p.q rides on the multiply; one partial per CTA, summed in a fixed order later
@@ -165,6 +171,127 @@ __global__ void __launch_bounds__(ROW_THREADS, RowCfg<T>::CTAS) spmv_cwalk_kerne
 #pragma unroll
             for (int w = 0; w < ROW_THREADS / 32; ++w) t += dsh[w];
             a.dot_out[blockIdx.x] = t;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sparse x dense on compact tiles: C[:, k0 .. k0+K) = A * B[:, k0 .. k0+K) for the interior tiles (A * B::HPCMatrix,
+// src/sparse.jl:2391-2413).  B is column-major, so the x runs of a tile are contiguous in EVERY column: the same run table
+// drives K bulk copies per run, the tile's values and 16-bit positions are fetched once for K right-hand sides, and the
+// walk reads all K operands of an entry from shared memory (the plain kernel issues K separate 8-byte gathers per entry).
+// ------------------------------------------------------------------------------------------------------------------
+template <class T>
+struct CWalkMArgs {
+    const T* nzval;
+    const unsigned char* hdrs;
+    const unsigned char* colpos;
+    const T* b_own;  // B's local block at its first own row, column k0 (16-byte aligned; ldb * sizeof(T) a multiple of 16)
+    i64 ldb;
+    T* c;  // C's local block, column k0
+    i64 ldc;
+    i64 nnz_total;
+    TileRuns runs;
+    int q0, tail_q_min;
+    int window, cw, chdr_bytes, chdr_fetch, cp_bytes, xcap;
+};
+
+__device__ __forceinline__ void mbar_add_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <class T, int G, int K>
+__global__ void __launch_bounds__(ROW_THREADS, K >= 8 ? 2 : K >= 4 ? 3 : RowCfg<T>::CTAS) spmm_cwalk_kernel(const CWalkMArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* barA = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* barB = barA + 1;
+    uint64_t* barX = barA + 2;
+    const unsigned char* shdr = smem_raw + 32;
+    const unsigned short* spos = reinterpret_cast<const unsigned short*>(smem_raw + 32 + a.chdr_bytes);
+    T* sval = reinterpret_cast<T*>(smem_raw + 32 + a.chdr_bytes + a.cp_bytes);
+    T* sx = sval + a.cw;  // [K][xcap]
+    const int tid = threadIdx.x;
+    const i64 tile = tile_of_cta(a.runs);
+    const i64 q = (i64)a.q0 + blockIdx.x;
+    const i64 w0 = tile * (i64)a.window;
+    const i64 left = (a.nnz_total - w0) & ~(i64)3;
+    const int n_fetch = (int)(left < (i64)a.cw ? (left > 0 ? left : 0) : (i64)a.cw);
+    const unsigned char* ghdr = a.hdrs + q * (i64)a.chdr_bytes;
+    if (tid == 0) {
+        mbar_init(barA, 1);
+        mbar_init(barB, 1);
+        mbar_init(barX, 32);
+        mbar_fence_init();
+        const uint64_t pol = l2_evict_first_policy();
+        mbar_expect_tx(barA, (uint32_t)a.chdr_fetch + (uint32_t)a.cp_bytes);
+        bulk_g2s(const_cast<unsigned char*>(shdr), ghdr, (uint32_t)a.chdr_fetch, barA, pol);
+        bulk_g2s(const_cast<unsigned short*>(spos), a.colpos + q * (i64)a.cp_bytes, (uint32_t)a.cp_bytes, barA, pol);
+        mbar_expect_tx(barB, (uint32_t)n_fetch * (uint32_t)sizeof(T));
+        if (n_fetch > 0) bulk_g2s(sval, a.nzval + w0, (uint32_t)n_fetch * (uint32_t)sizeof(T), barB, pol);
+    }
+    __syncthreads();
+    if (tid < 32) {  // K copies per x run, spread over the lanes of warp 0
+#pragma unroll
+        for (int idx = tid; idx < K * CW_R; idx += 32) {
+            const int k = idx / CW_R, j = idx % CW_R;
+            const int4 run = __ldg(reinterpret_cast<const int4*>(ghdr + 32) + j);
+            if (run.y > 0) {
+                const uint32_t bytes = (uint32_t)run.y * (uint32_t)sizeof(T);
+                mbar_add_tx(barX, bytes);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(sx + (size_t)k * a.xcap + run.z)),
+                             "l"(a.b_own + (i64)k * a.ldb + run.x), "r"(bytes), "r"(smem_u32(barX))
+                             : "memory");
+            }
+        }
+        mbar_arrive(barX);
+    }
+    mbar_wait(barA, 0);
+    const CHead* h = reinterpret_cast<const CHead*>(shdr);
+    const i64 r0 = h->r0;
+    const int nrows = h->nrows;
+    const unsigned short* off = reinterpret_cast<const unsigned short*>(shdr + CW_HDR_FIXED);
+    {
+        const i64 avail = a.nnz_total - w0;
+        const int n_avail = (int)(avail < (i64)a.cw ? avail : (i64)a.cw);
+        const bool x_tail = q >= (i64)a.tail_q_min, v_tail = n_fetch < n_avail;
+        if (x_tail || v_tail) {
+            if (x_tail && tid < h->tail_n * K) {
+                const int k = tid / h->tail_n, t = tid % h->tail_n;
+                sx[(size_t)k * a.xcap + h->tail_soff + t] = a.b_own[(i64)k * a.ldb + reinterpret_cast<const CRun*>(shdr + 32)->tail_xoff + t];
+            }
+            if (v_tail)
+                for (int kk = n_fetch + tid; kk < n_avail; kk += ROW_THREADS) sval[kk] = a.nzval[w0 + kk];
+            __syncthreads();
+        }
+    }
+    mbar_wait(barX, 0);
+    mbar_wait(barB, 0);
+    constexpr int RPP = ROW_THREADS / G;
+    const int lane = tid % G;
+    for (int base = 0; base < nrows; base += RPP) {
+        const int i = base + tid / G;
+        const bool valid = i < nrows;
+        const int b = valid ? (int)off[i] : 0;
+        const int e = valid ? (int)off[i + 1] : 0;
+        T acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = el_zero(T());
+        for (int kk = b + lane; kk < e; kk += G) {
+            const T v = sval[kk];
+            const T* xp = sx + spos[kk];
+#pragma unroll
+            for (int k = 0; k < K; ++k) acc[k] = el_add(acc[k], el_mul(v, xp[(size_t)k * a.xcap]));
+        }
+        if (G > 1) {
+#pragma unroll
+            for (int m = G / 2; m >= 1; m >>= 1)
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = el_add(acc[k], shfl_xor(acc[k], m));
+        }
+        if (valid && lane == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) st_y(a.c + r0 + i + (i64)k * a.ldc, acc[k]);
         }
     }
 }
@@ -383,6 +510,76 @@ cudaError_t launch_spmv_cwalk(const CWalkLaunch& L, cudaStream_t st) {
     if (L.dtype == HPCLA_F32) return cwalk_typed<float>(L, st);
     if (L.dtype == HPCLA_F64) return cwalk_typed<double>(L, st);
     if (L.dtype == HPCLA_C128) return cwalk_typed<cplx>(L, st);
+    return cudaErrorInvalidValue;
+}
+
+size_t cwalk_m_smem_bytes(int dtype, const CompactShape& sh, int K) {
+    const size_t ts = dtype == HPCLA_F32 ? 4 : dtype == HPCLA_F64 ? 8 : 16;
+    return 32 + (size_t)sh.chdr_bytes + (size_t)sh.cp_bytes + ((size_t)sh.cw + (size_t)K * sh.xcap) * ts;
+}
+
+template <class T, int G, int K>
+static cudaError_t cwalk_m_launch(const CWalkMLaunch& L, const CWalkMArgs<T>& a, cudaStream_t st) {
+    const size_t smem = cwalk_m_smem_bytes(L.dtype, L.sh, K);
+    cudaError_t e;
+    if ((e = ensure_smem<spmm_cwalk_kernel<T, G, K>>(smem, true)) != cudaSuccess) return e;
+    spmm_cwalk_kernel<T, G, K><<<L.n_launch, ROW_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <class T, int K>
+static cudaError_t cwalk_m_lanes(const CWalkMLaunch& L, cudaStream_t st) {
+    const size_t es = sizeof(T);
+    CWalkMArgs<T> a;
+    a.nzval = (const T*)L.nzval;
+    a.hdrs = L.hdrs;
+    a.colpos = L.colpos;
+    a.b_own = (const T*)L.b_own + (i64)L.k0 * L.ldb;
+    a.ldb = L.ldb;
+    a.c = (T*)L.c + (i64)L.k0 * L.ldc;
+    a.ldc = L.ldc;
+    a.nnz_total = L.nnz;
+    a.runs = launch_runs(L.n_runs, L.run_cta0, L.run_tile0);
+    a.q0 = L.q0;
+    a.tail_q_min = L.tail_q_min;
+    a.window = L.window;
+    a.cw = L.sh.cw;
+    a.chdr_bytes = L.sh.chdr_bytes;
+    a.chdr_fetch = L.sh.chdr_fetch;
+    a.cp_bytes = L.sh.cp_bytes;
+    a.xcap = L.sh.xcap;
+    (void)es;
+    switch (L.lanes) {
+        case 1: return cwalk_m_launch<T, 1, K>(L, a, st);
+        case 2: return cwalk_m_launch<T, 2, K>(L, a, st);
+        case 4: return cwalk_m_launch<T, 4, K>(L, a, st);
+        case 8: return cwalk_m_launch<T, 8, K>(L, a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <class T>
+static cudaError_t cwalk_m_typed(const CWalkMLaunch& L, cudaStream_t st) {
+    if (L.n_launch <= 0) return cudaSuccess;
+    if (L.kn == 8) return cwalk_m_lanes<T, 8>(L, st);
+    if (L.kn == 4) return cwalk_m_lanes<T, 4>(L, st);
+    if (L.kn == 1) return cwalk_m_lanes<T, 1>(L, st);
+    return cudaErrorInvalidValue;
+}
+
+// whether the compact kernel can take this launch: staged x for kn columns must fit the SM's shared memory, the lanes must
+// be a supported count, and every column's x runs must start on a 16-byte boundary
+bool spmm_cwalk_supported(const CWalkMLaunch& L) {
+    const size_t es = L.dtype == HPCLA_F32 ? 4 : L.dtype == HPCLA_F64 ? 8 : 16;
+    if (L.lanes < 1 || L.lanes > 8) return false;
+    if ((((uintptr_t)L.b_own) & 15) || ((L.ldb * (i64)es) & 15) || ((((uintptr_t)L.b_own) + (size_t)L.k0 * (size_t)L.ldb * es) & 15)) return false;
+    return cwalk_m_smem_bytes(L.dtype, L.sh, L.kn) <= 110 * 1024;
+}
+
+cudaError_t launch_spmm_cwalk(const CWalkMLaunch& L, cudaStream_t st) {
+    if (L.dtype == HPCLA_F32) return cwalk_m_typed<float>(L, st);
+    if (L.dtype == HPCLA_F64) return cwalk_m_typed<double>(L, st);
+    if (L.dtype == HPCLA_C128) return cwalk_m_typed<cplx>(L, st);
     return cudaErrorInvalidValue;
 }
 

@@ -3,8 +3,10 @@
 //   || interior row tiles (caller's stream)  ->  wait  ->  boundary row tiles + split long rows.
 // Replaces execute_plan! (src/vectors.jl:394-463: host-staged Isend/Irecv with a D2H copy of x and an H2D copy of
 // `gathered` per call) and the launch in Base.:*(A, x) / mul! (src/sparse.jl:2096-2128, 2019-2037).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <sched.h>
 #include <nccl.h>
 #include <nvtx3/nvToolsExt.h>
@@ -85,6 +87,25 @@ NcclApi* nccl_api() {
         if (_r != ncclSuccess) return fail(HPCLA_ERR_NCCL, "%s failed: %s", #expr, nccl_api()->GetErrorString(_r)); \
     } while (0)
 
+// Stream memory operations of the driver API (the runtime has no equivalent): a stream waits until a 32-bit word in
+// device memory reaches a value — no kernel spins, no SM is held.  Resolved through the runtime (cudaGetDriverEntryPoint):
+// the library does not link libcuda.
+namespace {
+typedef CUresult (*fn_stream_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+fn_stream_wait32 stream_wait32() {
+    static fn_stream_wait32 fn = []() -> fn_stream_wait32 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (fn_stream_wait32)p;
+    }();
+    return fn;
+}
+}  // namespace
+
 // Inside ncclGroupStart .. ncclGroupEnd: a failed call closes the group before the error is returned, so that later
 // NCCL calls of this thread are not queued behind a group that never ends.
 #define NCCL_TRY_IN_GROUP(expr)                                                                                    \
@@ -143,7 +164,7 @@ struct hpcla_csr {
     void* d_partials = nullptr;
     FlatData flat;        // irregular matrices: the nnz-split multiply (flat.cu); n_chunks == 0 otherwise
     bool flat_keep_x = false;  // gather x with an L2 evict-last hint (HPCLA_FLAT_KEEP_X)
-    bool flat_l2_window = true;  // pin the own segment of x in the persisting part of L2 during the launch (HPCLA_FLAT_L2_WINDOW=0: off)
+    bool flat_l2_window = false;  // pin the own segment of x in the persisting part of L2 during the launch (HPCLA_FLAT_L2_WINDOW=1; measured slower)
 };
 
 struct Seg {
@@ -193,6 +214,19 @@ struct hpcla_spmv {
     std::vector<int> h_list[3][2];  // host copies (block boundaries of the staged multiply)
     // every list as runs of consecutive tiles, found once: {first position in the list, first tile}, ascending
     std::vector<std::pair<int, int>> runs[3][2];
+    // Direct halo (hpcla_spmv_halo_*): ghosts are pushed straight into the peers' `gathered` over NVLink by the copy
+    // engine (peer memory mapped with CUDA IPC, or plain pointers inside one process) and announced with flags the
+    // receiving stream waits on; no NCCL kernel, no rendezvous.  flags: [p] = last step whose data from rank p has landed
+    // here; [nranks + p] = last step whose data rank p has finished reading (so its segment may be overwritten).
+    struct DirectHalo {
+        bool on = false;
+        unsigned* d_flags = nullptr;
+        std::vector<char*> peer_gathered;    // [nranks] base of rank p's `gathered` as seen from here (null: no exchange with p)
+        std::vector<unsigned*> peer_flags;   // [nranks]
+        std::vector<i64> peer_recv_start;    // [nranks] 1-based start, in rank p's gathered, of the segment I fill
+        std::vector<void*> ipc_opened;       // mappings to close
+        unsigned step = 0;
+    } direct;
     // compact tiles (compact.cu): headers and 16-bit positions, by position in list [2][0]
     CompactShape csh{};
     unsigned char *d_chdr = nullptr, *d_cpos = nullptr;
@@ -598,7 +632,7 @@ extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nr
         CU_TRY(flat_build(itype, d_rowptr, nrows, nnz, &A->flat, st));
         CU_TRY(cudaMalloc(&A->flat.d_heads, dtype_size(dtype) * (size_t)std::max<i64>(A->flat.n_wchunks, 1)));
         if (const char* e = getenv("HPCLA_FLAT_KEEP_X")) A->flat_keep_x = e[0] == '1';
-        if (const char* e = getenv("HPCLA_FLAT_L2_WINDOW")) A->flat_l2_window = e[0] != '0';
+        if (const char* e = getenv("HPCLA_FLAT_L2_WINDOW")) A->flat_l2_window = e[0] == '1';
     }
     // rows longer than the split threshold (rare: power-law tails)
     const i64 cap = nnz / A->long_threshold + 1;
@@ -904,6 +938,8 @@ extern "C" void hpcla_spmv_destroy(hpcla_spmv* op) {
         for (int g = 0; g < 2; ++g) cudaFree(op->d_list[c][g]);
     cudaFree(op->d_chdr);
     cudaFree(op->d_cpos);
+    for (void* q : op->direct.ipc_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(op->direct.d_flags);
     cudaFree(op->d_dot_partials);
     if (op->pipe) {
         for (cudaEvent_t e : op->pipe->ev_in) cudaEventDestroy(e);
@@ -932,6 +968,100 @@ static hpcla_spmv* group_peer(const hpcla_spmv* op, int peer) {
     std::lock_guard<std::mutex> lk(g->mu);
     if ((i64)g->ops.size() <= op->seq) return nullptr;
     return g->ops[(size_t)op->seq][(size_t)peer];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Direct halo: export / connect (collective through the host: every rank hands its blob to every other rank)
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct HaloBlobHead {
+    cudaIpcMemHandle_t mem, flags;
+    long long raw_gathered, raw_flags, pid, device;
+};
+static_assert(sizeof(HaloBlobHead) == 160, "blob header layout");
+}  // namespace
+
+extern "C" int hpcla_spmv_halo_blob_size(const hpcla_spmv* op, int64_t* bytes_out) {
+    if (!op || !bytes_out) return fail(HPCLA_ERR_ARG, "hpcla_spmv_halo_blob_size: null");
+    *bytes_out = (int64_t)sizeof(HaloBlobHead) + 8 * (int64_t)op->ctx->nranks;
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_halo_export(hpcla_spmv* op, void* blob_out) {
+    if (!op || !blob_out) return fail(HPCLA_ERR_ARG, "hpcla_spmv_halo_export: null");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    const int P = op->ctx->nranks;
+    if (!stream_wait32()) return fail(HPCLA_ERR_CUDA, "hpcla_spmv_halo_export: the driver offers no cuStreamWaitValue32");
+    if (!op->direct.d_flags) {
+        CU_TRY(cudaMalloc(&op->direct.d_flags, sizeof(unsigned) * 2 * (size_t)P));
+        CU_TRY(cudaMemset(op->direct.d_flags, 0, sizeof(unsigned) * 2 * (size_t)P));
+    }
+    HaloBlobHead h;
+    std::memset(&h, 0, sizeof h);
+    if (op->d_gathered) CU_TRY(cudaIpcGetMemHandle(&h.mem, op->d_gathered));
+    CU_TRY(cudaIpcGetMemHandle(&h.flags, op->direct.d_flags));
+    h.raw_gathered = (long long)(uintptr_t)op->d_gathered;
+    h.raw_flags = (long long)(uintptr_t)op->direct.d_flags;
+    h.pid = (long long)getpid();
+    h.device = op->ctx->device;
+    std::memcpy(blob_out, &h, sizeof h);
+    long long* starts = reinterpret_cast<long long*>((char*)blob_out + sizeof h);
+    for (int p = 0; p < P; ++p) starts[p] = 0;
+    for (const Seg& r : op->recvs) starts[r.peer] = r.start;  // where rank r.peer's data lands in my gathered
+    return HPCLA_OK;
+}
+
+extern "C" int hpcla_spmv_halo_connect(hpcla_spmv* op, const void* blobs) {
+    if (!op || !blobs) return fail(HPCLA_ERR_ARG, "hpcla_spmv_halo_connect: null");
+    if (!op->direct.d_flags) return fail(HPCLA_ERR_STATE, "hpcla_spmv_halo_connect: call hpcla_spmv_halo_export first");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    const int P = op->ctx->nranks, me = op->ctx->rank;
+    const size_t stride = sizeof(HaloBlobHead) + 8 * (size_t)P;
+    auto& D = op->direct;
+    D.peer_gathered.assign((size_t)P, nullptr);
+    D.peer_flags.assign((size_t)P, nullptr);
+    D.peer_recv_start.assign((size_t)P, 0);
+    std::vector<char> need((size_t)P, 0);
+    for (const Seg& sg : op->sends) need[(size_t)sg.peer] |= 1;  // I write its gathered and its arrival flag
+    for (const Seg& r : op->recvs) need[(size_t)r.peer] |= 2;   // I write its consumed flag
+    for (int p = 0; p < P; ++p) {
+        if (!need[(size_t)p] || p == me) continue;
+        HaloBlobHead h;
+        std::memcpy(&h, (const char*)blobs + (size_t)p * stride, sizeof h);
+        const long long* starts = reinterpret_cast<const long long*>((const char*)blobs + (size_t)p * stride + sizeof h);
+        D.peer_recv_start[(size_t)p] = starts[me];
+        if ((need[(size_t)p] & 1) && starts[me] <= 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_halo_connect: rank %d does not expect data from rank %d", p, me);
+        if (h.pid == (long long)getpid()) {  // same process (rank-threads): plain pointers (peer access was enabled with the group)
+            D.peer_gathered[(size_t)p] = (char*)(uintptr_t)h.raw_gathered;
+            D.peer_flags[(size_t)p] = (unsigned*)(uintptr_t)h.raw_flags;
+        } else {
+            void* q = nullptr;
+            if (need[(size_t)p] & 1) {
+                CU_TRY(cudaIpcOpenMemHandle(&q, h.mem, cudaIpcMemLazyEnablePeerAccess));
+                D.peer_gathered[(size_t)p] = (char*)q;
+                D.ipc_opened.push_back(q);
+            }
+            CU_TRY(cudaIpcOpenMemHandle(&q, h.flags, cudaIpcMemLazyEnablePeerAccess));
+            D.peer_flags[(size_t)p] = (unsigned*)q;
+            D.ipc_opened.push_back(q);
+        }
+    }
+    D.on = true;
+    return HPCLA_OK;
+}
+
+// the receiving side of the back-pressure: tell every rank I received from that its data of this step has been read
+static int direct_signal_consumed(hpcla_spmv* op, cudaStream_t stream) {
+    auto& D = op->direct;
+    if (!D.on) return HPCLA_OK;
+    const int P = op->ctx->nranks, me = op->ctx->rank;
+    for (const Seg& r : op->recvs) {
+        CU_TRY(launch_write_flag(D.peer_flags[(size_t)r.peer] + P + me, D.step, stream));
+        op->launches += 1;
+    }
+    return HPCLA_OK;
 }
 
 // Send half of the exchange, on the halo stream: wait for x, pack what is not contiguous, and (NCCL world) post the
@@ -971,6 +1101,34 @@ static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream, 
     }
     CU_TRY(cudaEventRecord(op->ev_packed, hs));
     op->epoch.fetch_add(1, std::memory_order_release);
+    if (op->direct.on) {
+        // push: every run goes straight into its segment of the peer's `gathered` (copy engine over NVLink), then the
+        // peer's arrival flag is raised; my own receives are awaited as flag values, not as kernels
+        auto& D = op->direct;
+        const int P = ctx->nranks, me = ctx->rank;
+        const unsigned step = ++D.step;
+        fn_stream_wait32 wait32 = stream_wait32();
+        for (const Seg& s : op->sends) {
+            // the peer has finished reading what I sent it last time
+            if (wait32((CUstream)hs, (CUdeviceptr)(uintptr_t)(D.d_flags + P + s.peer), step - 1, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail(HPCLA_ERR_CUDA, "cuStreamWaitValue32 failed");
+            const bool from_x = !group && op->sends_contiguous;
+            const char* src = from_x ? (const char*)d_x + (size_t)(s.src0 - 1) * es : (const char*)op->d_sendbuf + (size_t)s.start * es;
+            CU_TRY(cudaMemcpyAsync(D.peer_gathered[(size_t)s.peer] + (size_t)(D.peer_recv_start[(size_t)s.peer] - 1) * es, src, (size_t)s.count * es, cudaMemcpyDefault, hs));
+            CU_TRY(launch_write_flag(D.peer_flags[(size_t)s.peer] + me, step, hs));
+            op->launches += 1;
+        }
+        for (const Seg& r : op->recvs)
+            if (wait32((CUstream)hs, (CUdeviceptr)(uintptr_t)(D.d_flags + r.peer), step, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail(HPCLA_ERR_CUDA, "cuStreamWaitValue32 failed");
+        CU_TRY(cudaEventRecord(op->ev_halo, hs));
+        op->halo_recorded = true;
+        if (op->timeline) {
+            CU_TRY(cudaEventRecord(op->tl[1], hs));
+            op->tl_rec[1] = true;
+        }
+        return HPCLA_OK;
+    }
     if (!group && ctx->comm) {
         NcclApi* api = nccl_api();
         size_t per = 1;
@@ -1123,7 +1281,9 @@ static int launch_flat(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stre
     F.long_threshold = A->long_threshold;
     // x is the one array this multiply re-reads (every stored entry gathers from it) while 40x as many bytes of matrix
     // stream through L2: when the own segment of x fits, it is pinned in the persisting part of L2 for the duration of the
-    // launch (access-policy window on the stream; HPCLA_FLAT_L2_WINDOW=0 disables).
+    // launch (access-policy window on the stream).  Opt-in, HPCLA_FLAT_L2_WINDOW=1: measured, it cuts the DRAM traffic of BASELINE
+    // config 4 from 9.5 GB to 3.6 GB per multiply but makes the multiply SLOWER (3.1 ms against 2.3 ms: the set-aside part of
+    // L2 serves the gathers at a lower rate), profiles/r2c_*.
     bool window = false;
     const size_t xbytes = (size_t)op->own_n * dtype_size(A->dtype);
     if (A->flat_l2_window && base.x_own && xbytes > 0 && xbytes <= op->ctx->l2_persist_max) {
@@ -1246,7 +1406,7 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
     if (rc) return rc;
     cudaStream_t stream = op->cur_stream;
     cudaStream_t hs = op->ctx->halo_stream;
-    if (op->has_peers && op->ctx->group) {
+    if (op->has_peers && op->ctx->group && !op->direct.on) {
         rc = exchange_finish_group(op);
         if (rc) return rc;
     }
@@ -1283,6 +1443,8 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
         rc = launch_long(op, L, stream);
         if (rc) return rc;
     }
+    rc = direct_signal_consumed(op, stream);  // (direct halo) the ghosts of this step have been read
+    if (rc) return rc;
     if (op->timeline) {
         CU_TRY(cudaEventRecord(op->tl[4], stream));
         op->tl_rec[4] = true;
@@ -1320,6 +1482,7 @@ extern "C" int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d
     if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_graph_capture: null");
     if (op->ctx->group && op->ctx->nranks > 1 && op->has_peers) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: needs an NCCL world or a single rank");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: the previous call was not finished");
+    if (op->direct.on) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: the direct halo counts steps in its flags and cannot be replayed from a graph");
     int rc = set_device(op->ctx);
     if (rc) return rc;
     (void)stream_;  // the capture runs on a library-owned stream: the caller's may be the legacy default stream, which cannot be captured
@@ -1365,7 +1528,7 @@ extern "C" int hpcla_spmv_graph_launch(hpcla_spmv* op, void* stream_) {
 }
 
 extern "C" int hpcla_spmv_run(hpcla_spmv* op, const void* d_x, void* d_y, void* stream) {
-    if (op && op->ctx->group && op->ctx->nranks > 1 && op->has_peers)
+    if (op && op->ctx->group && op->ctx->nranks > 1 && op->has_peers && !op->direct.on)
         return fail(HPCLA_ERR_STATE, "hpcla_spmv_run: in a single-process world call hpcla_spmv_begin on every rank, then hpcla_spmv_finish");
     int rc = hpcla_spmv_begin(op, d_x, d_y, stream);
     if (rc) return rc;
@@ -1403,6 +1566,7 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
     const bool walk = spmm_supports_rowwalk(A->shape);
     // 8 columns per pass when there are that many (measured: 1 014 -> 918 us for 8 columns of Poisson 256^3); HPCLA_SPMM_K8=0 disables
     static const bool spmm_k8 = [] { const char* e = getenv("HPCLA_SPMM_K8"); return e ? e[0] != '0' : true; }();
+    static const bool spmm_compact = [] { const char* e = getenv("HPCLA_SPMM_COMPACT"); return e ? e[0] != '0' : true; }();
     for (int k0 = 0; k0 < op->mm_ncols;) {
         L.k0 = k0;
         const int left = op->mm_ncols - k0;
@@ -1411,7 +1575,35 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
             L.recs = op->d_list[c][which];
             L.n_launch = op->n_list[c][which];
             if (L.n_launch <= 0) continue;
-            tile_runs(op->runs[c][which], 0, L.n_launch, L);
+            const bool runs = tile_runs(op->runs[c][which], 0, L.n_launch, L);
+            if (c == 2 && runs && which == 0 && spmm_compact) {  // interior compact tiles: x runs of all kn columns staged by bulk copies
+                CWalkMLaunch M;
+                M.dtype = L.dtype;
+                M.lanes = L.shape.lanes;
+                M.window = L.shape.window;
+                M.nzval = L.nzval;
+                M.nnz = L.nnz;
+                M.sh = op->csh;
+                M.hdrs = op->d_chdr;
+                M.colpos = op->d_cpos;
+                M.q0 = 0;
+                M.tail_q_min = op->ctail_q_min;
+                M.n_runs = L.n_runs;
+                for (int j = 0; j < 9; ++j) M.run_cta0[j] = L.run_cta0[j];
+                for (int j = 0; j < 8; ++j) M.run_tile0[j] = L.run_tile0[j];
+                M.n_launch = L.n_launch;
+                M.b_own = L.b_own;
+                M.ldb = L.ldb;
+                M.c = L.c;
+                M.ldc = L.ldc;
+                M.k0 = L.k0;
+                M.kn = L.kn;
+                if (spmm_cwalk_supported(M)) {
+                    CU_TRY(launch_spmm_cwalk(M, stream));
+                    op->launches += 1;
+                    continue;
+                }
+            }
             if (c != 1 && walk) CU_TRY(launch_spmm_rowwalk(L, stream));
             else CU_TRY(launch_spmm_rows(L, stream));
             op->launches += 1;
@@ -1693,6 +1885,8 @@ extern "C" int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x,
     }
     CU_TRY(cudaEventRecord(P->ev_done, out));
     CU_TRY(cudaStreamWaitEvent(stream, P->ev_done, 0));  // the caller's stream now orders after host y is complete
+    rc = direct_signal_consumed(op, stream);
+    if (rc) return rc;
     return HPCLA_OK;
 }
 
@@ -1737,12 +1931,15 @@ extern "C" int hpcla_spmv_gather_finish(hpcla_spmv* op) {
     int rc = set_device(op->ctx);
     if (rc) return rc;
     if (op->has_peers) {
-        if (op->ctx->group) {
+        if (op->ctx->group && !op->direct.on) {
             rc = exchange_finish_group(op);
             if (rc) return rc;
         }
         CU_TRY(cudaStreamWaitEvent(op->cur_stream, op->ev_halo, 0));
         if (op->ctx->group) CU_TRY(cudaStreamWaitEvent(op->cur_stream, op->ev_packed, 0));
+        // (direct halo) `gathered` stays valid for the caller until the next exchange begins; the peers may overwrite it then
+        rc = direct_signal_consumed(op, op->cur_stream);
+        if (rc) return rc;
     }
     op->phase = 0;
     return HPCLA_OK;

@@ -149,6 +149,28 @@ struct CWalkLaunch {
     double* dot_out = nullptr;
 };
 cudaError_t launch_spmv_cwalk(const CWalkLaunch& L, cudaStream_t st);
+// sparse x dense on the same compact tiles: kn (8, 4 or 1) columns from column k0
+struct CWalkMLaunch {
+    int dtype, lanes, window;
+    const void* nzval;
+    i64 nnz;
+    CompactShape sh;
+    const unsigned char* hdrs;
+    const unsigned char* colpos;
+    int q0;
+    int tail_q_min = 0x7fffffff;
+    int n_runs = 0;
+    int run_cta0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int run_tile0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int n_launch;
+    const void* b_own;  // B's local block at its first own row, column 0
+    i64 ldb;
+    void* c;  // C's local block, column 0
+    i64 ldc;
+    int k0, kn;
+};
+bool spmm_cwalk_supported(const CWalkMLaunch& L);
+cudaError_t launch_spmm_cwalk(const CWalkMLaunch& L, cudaStream_t st);
 
 // nnz-split multiply for irregular matrices (flat.cu): per-matrix derived structure
 struct FlatData {
@@ -204,6 +226,8 @@ int ctx_rank_info(const hpcla_ctx* ctx, int* device, int* rank, int* nranks, int
 int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, const i64* send_bytes, void* d_recv, const i64* recv_off,
                        const i64* recv_bytes, cudaStream_t stream);
 
+// *flag = value after everything enqueued before it on the stream (system scope; the flag may live on a peer GPU)
+cudaError_t launch_write_flag(unsigned* flag, unsigned value, cudaStream_t st);
 // out[k] = x[idx[k]-1]          (pack of src/vectors.jl:431-437, all peers in one launch)
 cudaError_t launch_pack(int dtype, const void* x, const i64* idx, i64 n, void* out, cudaStream_t st);
 // gathered[dst[k]-1] = x[src[k]-1]   (local copy of src/vectors.jl:426-428 == _gather_kernel! :174-177)

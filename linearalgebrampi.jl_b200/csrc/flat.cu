@@ -116,7 +116,11 @@ template <class T, class Ti> struct FlatCfg {
     static constexpr int STAGE = 64 + FLAT_WCHUNK * (int)sizeof(Ti);
     static constexpr int FIT = (60 * 1024) / (2 * STAGE);
     static constexpr int BY_REGS = sizeof(T) <= 4 ? 16 : sizeof(T) <= 8 ? 12 : 6;  // x and values of two chunks live in registers
-    static constexpr int WARPS = FIT < BY_REGS ? FIT : BY_REGS;
+#ifndef HPCLA_FLAT_MAX_WARPS
+#define HPCLA_FLAT_MAX_WARPS 16  // A/B knob
+#endif
+    static constexpr int W0 = FIT < BY_REGS ? FIT : BY_REGS;
+    static constexpr int WARPS = W0 < HPCLA_FLAT_MAX_WARPS ? W0 : HPCLA_FLAT_MAX_WARPS;
     static constexpr bool PREFETCH = sizeof(T) <= 8;  // gathers and values of the next chunk in flight while this one is reduced
 };
 
@@ -188,89 +192,115 @@ __global__ void __launch_bounds__(FlatCfg<T, Ti>::WARPS * 32, 1) spmv_flat_kerne
         }
     };
     auto row_of = [&](i64 ord) -> i64 { return a.row_map ? __ldg(a.row_map + ord) : ord; };
-    // reduce warp chunk c (flags staged in s, x and values in registers) by row: register-level segmented scan, 4 rounds of
-    // 128 entries.  The lane boundaries of the scan come from one ballot (no flag shuffles); the common case of at most one
-    // row start among a lane's 4 entries is branch-free.
+    // reduce warp chunk c (flags staged in s, x and values in registers) by row: register-level segmented scan over 4 rounds of
+    // 128 entries.  The segment boundaries of each scan come from one ballot (no flag shuffles), and the four rounds' scans
+    // are independent of each other (only the short carry chain at the end is sequential), so they are issued interleaved:
+    // five dependent shuffle levels per chunk instead of twenty.  The common case of at most one row start among a
+    // lane's 4 entries is branch-free; rows shorter than 4 entries take a uniform slow path.
     auto reduce = [&](i64 c, int s, const T (&xg)[FLAT_ROUNDS][4], const T (&vg)[FLAT_ROUNDS][4], i64 wrow_c) {
         const int n_have = have(c);
         const unsigned* sbits = stage_bits(s);
         const int first_flag = (int)(sbits[0] & 1u);
-        i64 ord_open = wrow_c - first_flag;  // ordinal of the row that is open in front of this round's first entry
-        T carry = el_zero(T());              // its partial sum so far (within this warp chunk)
-        bool chunk_seen = false;             // a row start has been met in this warp chunk
+        T head[FLAT_ROUNDS], sv[FLAT_ROUNDS];
+        unsigned f[FLAT_ROUNDS], seen_mask[FLAT_ROUNDS];
+        int nbefore[FLAT_ROUNDS], ntotal[FLAT_ROUNDS], seg_lo[FLAT_ROUNDS];
+        bool any_short = false;
+#pragma unroll
+        for (int j = 0; j < FLAT_ROUNDS; ++j) {
+            const int e = 128 * j + 4 * lane;
+            f[j] = (e < n_have) ? (sbits[4 * j + (lane >> 3)] >> (4 * (lane & 7))) & 0xFu : 0u;
+            any_short = any_short || __popc(f[j]) > 1;
+        }
+        const bool slow = __any_sync(0xffffffffu, any_short);  // rows that start AND end inside one lane's 4 entries (rare)
+        i64 ord0 = wrow_c - first_flag;  // ordinal of the row that is open in front of the chunk's first entry
 #pragma unroll
         for (int j = 0; j < FLAT_ROUNDS; ++j) {
             const int e = 128 * j + 4 * lane;
             T p[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) p[k] = (e + k < n_have) ? el_mul(vg[j][k], xg[j][k]) : el_zero(T());
-            const unsigned f = (e < n_have) ? (sbits[4 * j + (lane >> 3)] >> (4 * (lane & 7))) & 0xFu : 0u;
-            const int nf = __popc(f);
             // row starts in front of my entries in this round, and in the whole round
-            const unsigned b0 = __ballot_sync(0xffffffffu, f & 1u), b1 = __ballot_sync(0xffffffffu, f & 2u);
-            const unsigned b2 = __ballot_sync(0xffffffffu, f & 4u), b3 = __ballot_sync(0xffffffffu, f & 8u);
-            const int nbefore = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-            const int ntotal = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+            const unsigned b0 = __ballot_sync(0xffffffffu, f[j] & 1u), b1 = __ballot_sync(0xffffffffu, f[j] & 2u);
+            const unsigned b2 = __ballot_sync(0xffffffffu, f[j] & 4u), b3 = __ballot_sync(0xffffffffu, f[j] & 8u);
+            nbefore[j] = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+            ntotal[j] = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+            const bool seen = f[j] != 0u;
             // my 4 entries: head = what belongs to the row open in front of me, tail = what my last row start has so far
-            T head, tail;
-            const bool seen = nf > 0;
-            if (__any_sync(0xffffffffu, nf > 1)) {  // rare (rows shorter than 4 entries): rows that start AND end inside my 4 entries
+            T tail;
+            if (slow) {
                 T acc = el_zero(T());
-                head = el_zero(T());
+                head[j] = el_zero(T());
                 bool sn = false;
-                i64 cur = ord_open + nbefore;
+                i64 ord_open = ord0;
+#pragma unroll
+                for (int jj = 0; jj < FLAT_ROUNDS; ++jj)
+                    if (jj < j) ord_open += ntotal[jj];
+                i64 cur = ord_open + nbefore[j];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if ((f >> k) & 1u) {
-                        if (!sn) head = acc, sn = true;
-                        else st_y(a.y + row_of(cur), acc);
+                    if ((f[j] >> k) & 1u) {
+                        if (!sn) head[j] = acc, sn = true;
+                        else st_y(a.y + row_of(cur), acc);  // a row inside my 4 entries: complete
                         cur += 1;
                         acc = p[k];
                     } else {
                         acc = el_add(acc, p[k]);
                     }
                 }
-                if (!sn) head = acc;
+                if (!sn) head[j] = acc;
                 tail = acc;
             } else {
-                const int pos = seen ? __ffs((int)f) - 1 : 4;  // my (only) row start
-                head = el_zero(T());
+                const int pos = seen ? __ffs((int)f[j]) - 1 : 4;  // my (only) row start
+                head[j] = el_zero(T());
                 tail = el_zero(T());
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    head = el_add(head, k < pos ? p[k] : el_zero(T()));
+                    head[j] = el_add(head[j], k < pos ? p[k] : el_zero(T()));
                     tail = el_add(tail, k >= pos ? p[k] : el_zero(T()));
                 }
-                if (!seen) tail = head;
+                if (!seen) tail = head[j];
             }
-            // segmented inclusive scan of the tails over the lanes (a lane with a row start begins a new segment)
-            const unsigned seen_mask = __ballot_sync(0xffffffffu, seen);
-            const unsigned below = seen_mask & (lt | (1u << lane));     // lanes with a row start, up to and including me
-            const int seg_lo = below ? 31 - __clz((int)below) : 0;     // first lane of my segment
-            T sv = tail;
+            seen_mask[j] = __ballot_sync(0xffffffffu, seen);
+            const unsigned below = seen_mask[j] & (lt | (1u << lane));  // lanes with a row start, up to and including me
+            seg_lo[j] = below ? 31 - __clz((int)below) : 0;            // first lane of my segment
+            sv[j] = tail;
+        }
+        // segmented inclusive scans of the tails over the lanes, the four rounds interleaved
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const T vu = shfl_up(sv, d);
-                if (lane - d >= seg_lo) sv = el_add(vu, sv);
-            }
-            const T pv = shfl_up(sv, 1);
-            const bool pf = (seen_mask & lt) != 0u;
+        for (int d = 1; d < 32; d <<= 1) {
+            T vu[FLAT_ROUNDS];
+#pragma unroll
+            for (int j = 0; j < FLAT_ROUNDS; ++j) vu[j] = shfl_up(sv[j], d);
+#pragma unroll
+            for (int j = 0; j < FLAT_ROUNDS; ++j)
+                if (lane - d >= seg_lo[j]) sv[j] = el_add(vu[j], sv[j]);
+        }
+        T pv[FLAT_ROUNDS], lastv[FLAT_ROUNDS];
+#pragma unroll
+        for (int j = 0; j < FLAT_ROUNDS; ++j) pv[j] = shfl_up(sv[j], 1), lastv[j] = shfl_idx(sv[j], 31);
+        // the carry chain across the rounds
+        i64 ord_open = ord0;
+        T carry = el_zero(T());   // partial sum of the open row so far (within this warp chunk)
+        bool chunk_seen = false;  // a row start has been met in this warp chunk
+#pragma unroll
+        for (int j = 0; j < FLAT_ROUNDS; ++j) {
+            const bool seen = f[j] != 0u;
+            const bool pf = (seen_mask[j] & lt) != 0u;
             T cin = carry;
             bool before_seen = chunk_seen;
             if (lane > 0) {
-                cin = pf ? pv : el_add(carry, pv);
+                cin = pf ? pv[j] : el_add(carry, pv[j]);
                 before_seen = chunk_seen || pf;
             }
             if (seen) {  // the row open in front of me ends at my first row start
-                const T total = el_add(cin, head);
-                if (before_seen) st_y(a.y + row_of(ord_open + nbefore), total);
+                const T total = el_add(cin, head[j]);
+                if (before_seen) st_y(a.y + row_of(ord_open + nbefore[j]), total);
                 else a.heads[c] = total;  // it began before this warp chunk (0 if the chunk begins with a row start)
             }
-            const T lastv = shfl_idx(sv, 31);
-            const bool lastf = seen_mask != 0u;
-            carry = lastf ? lastv : el_add(carry, lastv);
+            const bool lastf = seen_mask[j] != 0u;
+            carry = lastf ? lastv[j] : el_add(carry, lastv[j]);
             chunk_seen = chunk_seen || lastf;
-            ord_open += ntotal;
+            ord_open += ntotal[j];
         }
         if (lane == 0) {  // the row still open at the end of the warp chunk
             if (chunk_seen) st_y(a.y + row_of(ord_open), carry);  // it began here: its first part; the following heads are added by the fix-up

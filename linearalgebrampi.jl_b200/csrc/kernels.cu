@@ -487,6 +487,17 @@ __global__ void __launch_bounds__(256) tile_maxcol_kernel(const Ti* __restrict__
     }
 }
 
+// Direct halo: raise a flag in (possibly peer) memory once everything before it in the stream — the copy-engine push of
+// the ghost values — is complete.  System-scope release: the flag may be polled by another GPU's front end.
+__global__ void write_flag_kernel(unsigned* flag, unsigned value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+cudaError_t launch_write_flag(unsigned* flag, unsigned value, cudaStream_t st) {
+    write_flag_kernel<<<1, 1, 0, st>>>(flag, value);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // halo pack / local copy
 // ------------------------------------------------------------------------------------------------------------------

@@ -523,6 +523,26 @@ def mul_graph(y: HPCVector, A: HPCSparseMatrix, x: HPCVector) -> HPCVector:
     return y
 
 
+def enable_direct_halo(A: HPCSparseMatrix, x: HPCVector) -> None:
+    """Switch the halo exchange of (A, x.partition) from grouped ncclSend/ncclRecv to the direct push: every rank maps its
+    neighbours' `gathered` buffers (CUDA IPC between processes, plain pointers between rank-threads) and from then on
+    copies its ghost runs straight into them over NVLink with the copy engine, announcing them with flags the receiving
+    stream waits on (no kernel spins).  Collective: every rank exports a blob, the host communicator all-gathers them
+    (like the 128-byte NCCL id of ext/HPCLinearAlgebraCUDAExt.jl:411-443), every rank connects.  NCCL stays the default."""
+    L = _lib.lib()
+    op = _bound_op(A, get_vector_plan(A, x), x)
+    nbytes = ctypes.c_int64()
+    _lib.check(L.hpcla_spmv_halo_blob_size(op, ctypes.byref(nbytes)))
+    blob = np.zeros(nbytes.value, dtype=np.uint8)
+    _lib.check(L.hpcla_spmv_halo_export(op, _lib.ptr(blob)))
+    blobs = comm_allgather(A.backend.comm, blob.tobytes())
+    allb = np.frombuffer(b"".join(blobs), dtype=np.uint8).copy()
+    comm_barrier(A.backend.comm)
+    _lib.check(L.hpcla_spmv_halo_connect(op, _lib.ptr(allb)))
+    comm_barrier(A.backend.comm)
+    A._graphs.clear()
+
+
 def spmv_timeline(A: HPCSparseMatrix, x: HPCVector) -> Dict[str, float]:
     """Timeline of the most recent multiply (operators created under HPCLA_TIMELINE=1): milliseconds from 'x ready' to
     the end of the halo exchange, of the boundary tiles, of the interior tiles and of the call."""

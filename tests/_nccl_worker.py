@@ -183,6 +183,29 @@ def main():
     G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
     ref = orc.matvec(orc.distribute(G, P, itype="i32"), S.vector_local(np.float32, S.X_SEED, 0, n))
     assert relerr((A * x).to_global(), ref) <= 1e-5, "power-law rows over NCCL"
+    # 6. direct halo between processes: `gathered` and the flags mapped with CUDA IPC, ghosts pushed by the copy engine
+    b = la.backend_cuda_mpi(np.float64, np.int32, comm=comm, device=local_rank)
+    N = 36
+    n = N**3
+    A = S.stencil_matrix(1, N, b)
+    x = S.vector(n, b)
+    y_nccl = (A * x).to_global()
+    la.enable_direct_halo(A, x)
+    for k in range(5):
+        x.v.mul_(-1.0 if k else 1.0)
+        yk = (A * x).to_global()
+        assert np.array_equal(yk, (y_nccl if k % 2 == 0 else -y_nccl)), ("direct halo step", k)
+    sol_d, hist_d = la.cg(A, A * la.HPCVector.from_global(np.ones(n), b), 10)
+    A3 = S.stencil_matrix(1, N, b)  # the same system over NCCL
+    sol_n, hist_n = la.cg(A3, A3 * la.HPCVector.from_global(np.ones(n), b), 10)
+    assert np.array_equal(hist_d, hist_n), "CG over the direct halo == CG over NCCL"
+    xh2, yh2 = la.host_buffer(b, x.local_size), la.host_buffer(b, x.local_size)
+    xh2.array[:] = x.local_values()
+    x4, y4 = la.HPCVector.zeros(b, n), la.HPCVector.zeros(b, n)
+    for _ in range(2):
+        la.mul_staged(y4, A, x4, xh2.array, yh2.array)
+        torch.cuda.synchronize()
+    assert np.array_equal(y4.to_global(), -y_nccl), "staged multiply over the direct halo"
     dist.barrier()
     print("NCCL_OK", flush=True)
     dist.destroy_process_group()

@@ -413,3 +413,100 @@ def test_full_size_powerlaw_20m():
     err = np.abs(y - y_ref)
     scale = np.maximum(np.abs(y_ref), 1.0)
     assert float(np.max(err / scale)) <= 1e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sparse x dense on compact tiles
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,N,T,Ti", [(1, 40, np.float64, np.int32), (1, 33, np.float32, np.int64), (2, 20, np.float64, np.int32), (2, 16, np.complex128, np.int64)])
+@pytest.mark.parametrize("P", [1, 2])
+def test_sparse_times_dense_on_compact_tiles(kind, N, T, Ti, P, monkeypatch):
+    """A * B::HPCMatrix with the interior tiles on the compact kernel (x runs of all columns staged by bulk copies):
+    every column equals A * B[:, k] bit for bit, 13 columns = one pass of 8, one of 4 and one single column."""
+    monkeypatch.setenv("HPCLA_COMPACT", "1")
+    S = la.synth
+    n = S.stencil_rows(kind, N)
+    ncols = 13
+    rp, c, v = S.stencil_local(kind, N, 0, n, T, Ti)
+    G = sp.csr_matrix((v, c.astype(np.int64) - 1, rp.astype(np.int64) - 1), shape=(n, n))
+    Bg = np.stack([S.vector_local(T, S.X_SEED + j, 0, n) for j in range(ncols)], axis=1)
+
+    def body(rank, bs):
+        b = bs[rank]
+        torch.cuda.set_device(b.torch_device())
+        A = S.stencil_matrix(kind, N, b)
+        B = la.HPCMatrix.from_global(Bg, b)
+        C = A * B
+        cols = [(A * B.column(j)).to_global() for j in (0, 5, 12)]
+        return C.to_global(), cols, la.spmv_info(A, B.column(0))
+
+    la.clear_plan_cache()
+    res = spmd(backends(P, T, Ti), body)
+    ref = orc.matmat(orc.distribute(G, P, itype=_itype(Ti)), Bg)
+    for Cg, cols, info in res:
+        assert info["compact_tiles"] > 0
+        assert relerr(Cg, ref) <= TOL[np.dtype(T)]
+        for j, col in zip((0, 5, 12), cols):
+            assert np.array_equal(Cg[:, j], col), j
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# direct halo (peer push + flags instead of ncclSend/ncclRecv); here between the rank-threads of one process
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("P", [2, 3])
+def test_direct_halo_between_rank_threads(P):
+    S = la.synth
+    N = 30
+    n = N**3
+    rp, c, v = S.stencil_local(1, N, 0, n, np.float64, np.int32)
+    G = sp.csr_matrix((v, c - 1, rp - 1), shape=(n, n))
+    xh = S.vector_local(np.float64, S.X_SEED, 0, n)
+    rng = np.random.default_rng(31)
+    R = sp.random(1800, 1500, density=0.01, random_state=rng, format="csr")
+    R.data = rng.uniform(-1, 1, R.nnz)
+    R = (R @ sp.diags((np.arange(1500) % 3 != 1).astype(np.float64))).tocsr()  # send runs with holes -> pack kernel
+    R.eliminate_zeros()
+    xr = rng.uniform(-1, 1, 1500)
+    xp = np.concatenate([[1], np.sort(rng.integers(1, 1501, size=P - 1)), [1501]]).astype(np.int64)
+
+    def body(rank, bs):
+        b = bs[rank]
+        torch.cuda.set_device(b.torch_device())
+        A = S.stencil_matrix(1, N, b)
+        x = S.vector(n, b)
+        y_nccl_free = (A * x).to_global()  # rank-thread exchange (device-to-device copies pulled by the receiver)
+        la.enable_direct_halo(A, x)
+        ys = []
+        for k in range(4):  # back-to-back steps: the flags count steps, the consumed flags hold back the next push
+            x.v.mul_(-1.0 if k else 1.0)
+            ys.append((A * x).to_global())
+        g = la.execute_plan(la.get_vector_plan(A, x), A, x)
+        torch.cuda.synchronize()
+        gath = g.cpu().numpy().copy()
+        y_after = (A * x).to_global()
+        A2 = la.HPCSparseMatrix.from_global(R, b)
+        x2 = la.HPCVector.from_global(xr, b, partition=xp)
+        la.enable_direct_halo(A2, x2)
+        y2 = [(A2 * x2).to_global() for _ in range(2)]
+        return y_nccl_free, ys, gath, y_after, y2, la.spmv_info(A2, x2)
+
+    la.clear_plan_cache()
+    res = spmd(backends(P, np.float64, np.int32), body)
+    olocs = orc.distribute(G, P, itype="i32")
+    y_ref = orc.matvec(olocs, xh)
+    part = orc.uniform_partition(n, P)
+    W = orc.PlanWorld(olocs, part)
+    g_ref = W.execute(orc.split_vector(-xh, part))  # x was negated an odd number of times before the gather
+    W.close()
+    y2_ref = orc.matvec(orc.distribute(R, P, itype="i32"), xr, xp)
+    for r, (y0, ys, gath, y_after, y2, info2) in enumerate(res):
+        assert np.array_equal(y0, y_ref)
+        sign = 1.0
+        for k, y in enumerate(ys):
+            sign *= -1.0 if k else 1.0
+            assert np.array_equal(y, sign * y_ref), k
+        assert np.array_equal(gath, g_ref[r])
+        assert np.array_equal(y_after, -y_ref)
+        assert info2["sends_contiguous"] == 0
+        for y in y2:
+            assert relerr(y, y2_ref) <= 1e-12
