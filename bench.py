@@ -324,6 +324,8 @@ def run_b200_arm(args, spec):
     plan = la.get_vector_plan(Aop, x)
     L = la._lib.lib()
     opnd = la.sparse._bound_op(Aop, plan, x)
+    if args.halo == "direct" and world > 1:
+        la.enable_direct_halo(Aop, x)  # ghosts pushed into the neighbours' buffers by the copy engine + flags (NCCL is the default)
     info = la.spmv_info(Aop, x)
     setup_s = time.time() - t_setup
 
@@ -563,7 +565,7 @@ def run_b200_arm(args, spec):
                        "compact_tiles": info["compact_tiles"], "flat_chunks": info["flat_chunks"], "x_in_place": info["x_in_place"],
                        "lanes_per_row": info["lanes_per_row"], "tile_window": info["tile_window"], "rowwalk_tiles": info["rowwalk_tiles"],
                        "general_tiles": info["general_tiles"], "long_rows": info["long_rows"], "setup_s": round(setup_s, 2),
-                       "cuda_graph": bool(args.graph), "timeline": timeline},
+                       "cuda_graph": bool(args.graph), "halo": args.halo if world > 1 else "none", "timeline": timeline},
             "achieved_gbs": gbs, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(region),
         }
@@ -581,6 +583,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "direct"], help="halo exchange: grouped ncclSend/ncclRecv (default) or the direct peer push")
     ap.add_argument("--graph", action="store_true", help="replay each multiply (or the whole CG loop) from a CUDA graph")
     ap.add_argument("--timeline", action="store_true", help="record the per-rank timeline of one multiply (HPCLA_TIMELINE=1) into detail.timeline")
     ap.add_argument("--cpu-workers", type=int, default=0, help="worker threads of the CPU arm (0 = one per host core; 4 for the 2-D Laplacian, as BASELINE.json)")

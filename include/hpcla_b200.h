@@ -195,6 +195,9 @@ int hpcla_spmv_graph_launch(hpcla_spmv* op, void* stream);
 int hpcla_spmv_halo_blob_size(const hpcla_spmv* op, int64_t* bytes_out);
 int hpcla_spmv_halo_export(hpcla_spmv* op, void* blob_out);
 int hpcla_spmv_halo_connect(hpcla_spmv* op, const void* blobs /* nranks blobs, rank order */);
+/* debugging aid: out[0 .. nranks) = last step whose data from each rank has landed, out[nranks .. 2 nranks) = last step each
+ * rank has finished reading, out[2 nranks] = this rank's step counter; read on a private stream */
+int hpcla_spmv_halo_debug(hpcla_spmv* op, unsigned* out);
 /* Timeline of the most recent multiply, for operators created with HPCLA_TIMELINE=1 in the environment: milliseconds
  * from "x ready on the caller's stream" to the end of [0] the halo exchange, [1] the boundary tiles (both on the halo
  * stream), [2] the interior tiles, [3] the whole call (caller's stream); -1 where a step does not exist.  Blocks. */

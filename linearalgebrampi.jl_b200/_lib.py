@@ -89,6 +89,7 @@ SIGNATURES = {
     "hpcla_spmv_halo_blob_size": (_i, [_vp, _vp]),
     "hpcla_spmv_halo_export": (_i, [_vp, _vp]),
     "hpcla_spmv_halo_connect": (_i, [_vp, _vp]),
+    "hpcla_spmv_halo_debug": (_i, [_vp, _vp]),
     "hpcla_spmv_begin": (_i, [_vp, _vp, _vp, _vp]),
     "hpcla_spmv_finish": (_i, [_vp]),
     "hpcla_spmm_run": (_i, [_vp, _vp, _i64, _vp, _i64, _i, _vp]),

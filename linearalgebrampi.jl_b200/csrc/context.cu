@@ -1023,6 +1023,17 @@ extern "C" int hpcla_spmv_halo_connect(hpcla_spmv* op, const void* blobs) {
     D.peer_gathered.assign((size_t)P, nullptr);
     D.peer_flags.assign((size_t)P, nullptr);
     D.peer_recv_start.assign((size_t)P, 0);
+    // Everything the exchange paths allocate lazily is allocated now: once streams may sit in a flag wait, a call that
+    // synchronises the device (cudaMalloc / cudaFree) on one rank-thread of a single-process world would wait for a peer's
+    // halo stream, which waits for this thread's push — a deadlock.  (Between processes each has its own context.)
+    CU_TRY(preload_halo_kernels());
+    if (!op->d_local_src && op->own_n > 0) {
+        const hpcla_plan& PL = op->plan;
+        CU_TRY(cudaMalloc(&op->d_local_src, sizeof(i64) * (size_t)op->own_n));
+        CU_TRY(cudaMalloc(&op->d_local_dst, sizeof(i64) * (size_t)op->own_n));
+        CU_TRY(cudaMemcpy(op->d_local_src, PL.local_src.data(), sizeof(i64) * (size_t)op->own_n, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(op->d_local_dst, PL.local_dst.data(), sizeof(i64) * (size_t)op->own_n, cudaMemcpyHostToDevice));
+    }
     std::vector<char> need((size_t)P, 0);
     for (const Seg& sg : op->sends) need[(size_t)sg.peer] |= 1;  // I write its gathered and its arrival flag
     for (const Seg& r : op->recvs) need[(size_t)r.peer] |= 2;   // I write its consumed flag
@@ -1052,6 +1063,21 @@ extern "C" int hpcla_spmv_halo_connect(hpcla_spmv* op, const void* blobs) {
     return HPCLA_OK;
 }
 
+// debugging aid: the direct halo's flags and step counter, read on a private stream (works while other streams are blocked)
+extern "C" int hpcla_spmv_halo_debug(hpcla_spmv* op, unsigned* out /* [2 * nranks + 1] */) {
+    if (!op || !out || !op->direct.d_flags) return fail(HPCLA_ERR_ARG, "hpcla_spmv_halo_debug: no direct halo");
+    int rc = set_device(op->ctx);
+    if (rc) return rc;
+    cudaStream_t st;
+    CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const int P = op->ctx->nranks;
+    CU_TRY(cudaMemcpyAsync(out, op->direct.d_flags, sizeof(unsigned) * 2 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    cudaStreamDestroy(st);
+    out[2 * P] = op->direct.step;
+    return HPCLA_OK;
+}
+
 // the receiving side of the back-pressure: tell every rank I received from that its data of this step has been read
 static int direct_signal_consumed(hpcla_spmv* op, cudaStream_t stream) {
     auto& D = op->direct;
@@ -1078,7 +1104,7 @@ static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream, 
         CU_TRY(cudaStreamWaitEvent(hs, op->ev_x, 0));
     }
     const bool group = ctx->group != nullptr;
-    if (group) {
+    if (group && !op->direct.on) {  // (pull model only: with the direct halo I push, nobody reads my packed buffer)
         // my packed buffer may still be read by a peer's copy of the previous multiply
         for (const Seg& s : op->sends) {
             hpcla_spmv* peer = group_peer(op, s.peer);
@@ -2074,7 +2100,9 @@ extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work
     // p.q rides on the multiply when every row goes through the row-walk kernel (stencil-like matrices): the multiply
     // leaves one partial per CTA, a one-CTA kernel adds them in a fixed order — p and q are not read a second time
     const i64 n_partials = (i64)op->n_list[0][0] + op->n_list[2][0] + op->n_list[0][1];
-    const bool fused = op->n_list[1][0] + op->n_list[1][1] == 0 && op->csr->nlong == 0 && op->csr->flat.n_chunks == 0 && op->x_in_place &&
+    // (not with compact tiles: there the walk runs out of shared memory and the extra global load of p per row costs more
+    // than the separate dot kernel saves — measured 570 vs 488 us per iteration on Poisson 256^3, profiles/r2e_*)
+    const bool fused = op->n_list[1][0] + op->n_list[1][1] == 0 && op->n_list[2][0] == 0 && op->csr->nlong == 0 && op->csr->flat.n_chunks == 0 && op->x_in_place &&
                        op->own_src0 == 1 && n_partials > 0 && !getenv("HPCLA_CG_UNFUSED");
     if (fused && !op->d_dot_partials) CU_TRY(cudaMalloc(&op->d_dot_partials, sizeof(double) * (size_t)n_partials));
     // HPCLA_CG_GRAPH=1: the whole loop (iters x {multiply + halo, p.q, Allreduce, x/r update, Allreduce, p update}) as ONE

@@ -228,6 +228,7 @@ int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, 
 
 // *flag = value after everything enqueued before it on the stream (system scope; the flag may live on a peer GPU)
 cudaError_t launch_write_flag(unsigned* flag, unsigned value, cudaStream_t st);
+cudaError_t preload_halo_kernels();
 // out[k] = x[idx[k]-1]          (pack of src/vectors.jl:431-437, all peers in one launch)
 cudaError_t launch_pack(int dtype, const void* x, const i64* idx, i64 n, void* out, cudaStream_t st);
 // gathered[dst[k]-1] = x[src[k]-1]   (local copy of src/vectors.jl:426-428 == _gather_kernel! :174-177)

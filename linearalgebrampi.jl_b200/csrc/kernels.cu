@@ -487,11 +487,29 @@ __global__ void __launch_bounds__(256) tile_maxcol_kernel(const Ti* __restrict__
     }
 }
 
+template <class T> __global__ void pack_kernel(const T* __restrict__ x, const i64* __restrict__ idx, i64 n, T* __restrict__ out);
+template <class T> __global__ void local_copy_kernel(const T* __restrict__ x, const i64* __restrict__ src, const i64* __restrict__ dst, i64 n, T* __restrict__ g);
+
 // Direct halo: raise a flag in (possibly peer) memory once everything before it in the stream — the copy-engine push of
 // the ghost values — is complete.  System-scope release: the flag may be polled by another GPU's front end.
 __global__ void write_flag_kernel(unsigned* flag, unsigned value) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+// Loads (CUDA loads kernels lazily, on first launch, and a load synchronises the context) every kernel an exchange may
+// launch for the first time while some stream already sits in a flag wait: between the rank-threads of one process such a
+// load would wait for a halo stream that waits for a push this very thread has not enqueued yet.
+cudaError_t preload_halo_kernels() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+    if ((e = cudaFuncGetAttributes(&a, write_flag_kernel)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, pack_kernel<float>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, pack_kernel<double>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, pack_kernel<double2>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, local_copy_kernel<float>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, local_copy_kernel<double>)) != cudaSuccess) return e;
+    if ((e = cudaFuncGetAttributes(&a, local_copy_kernel<double2>)) != cudaSuccess) return e;
+    return cudaSuccess;
 }
 cudaError_t launch_write_flag(unsigned* flag, unsigned value, cudaStream_t st) {
     write_flag_kernel<<<1, 1, 0, st>>>(flag, value);

@@ -205,7 +205,7 @@ def main():
     for _ in range(2):
         la.mul_staged(y4, A, x4, xh2.array, yh2.array)
         torch.cuda.synchronize()
-    assert np.array_equal(y4.to_global(), -y_nccl), "staged multiply over the direct halo"
+    assert np.array_equal(y4.to_global(), y_nccl), "staged multiply over the direct halo"
     dist.barrier()
     print("NCCL_OK", flush=True)
     dist.destroy_process_group()

@@ -5,6 +5,13 @@ import sys
 import numpy as np
 import pytest
 
+# rank-threads of one process share one GPU in the single-GPU tests: give every stream its own hardware queue, so that a
+# halo stream waiting for a peer's flag can never sit in front of that peer's own work (set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and load every kernel up front: a lazy load (first launch) synchronises the context, which between rank-threads of
+# one process can wait for a halo stream that waits for this very thread (direct halo; not an issue between processes)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

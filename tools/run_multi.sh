@@ -29,10 +29,13 @@ for N in 2 4 8; do
   run_bench $N weak --timeline
   run_bench $N weak_graph --graph
   HPCLA_NCCL_MAX_CTAS=2 run_bench $N weak_ctas2
+  run_bench $N weak_direct --halo direct --timeline
   run_bench $N strong256 --workload poisson256-strong --timeline
+  run_bench $N strong256_direct --workload poisson256-strong --halo direct --timeline
   run_bench $N strong256_graph --workload poisson256-strong --graph
   run_bench $N cg --workload cg-512
   run_bench $N cg_graph --workload cg-512 --graph
+  run_bench $N cg_direct --workload cg-512 --halo direct
 done
 if [ $NMAX -ge 8 ]; then
   run_bench 8 strong512 --workload poisson512-strong
