@@ -264,6 +264,9 @@ def oracle_check(spec, rank, row_partition, y_local, x_seed, transpose=False, n_
 def run_b200_arm(args, spec):
     if args.timeline:
         os.environ["HPCLA_TIMELINE"] = "1"
+        args.graph = False  # (timing events are not part of a captured graph)
+    if args.halo == "direct":
+        args.graph = False  # (the direct halo counts steps in its flags: no replay)
     if args.graph:
         os.environ["HPCLA_CG_GRAPH"] = "1"
     import torch
@@ -443,7 +446,11 @@ def run_b200_arm(args, spec):
     gbs = bytes_step / (ms_per_step * 1e-3) / 1e9
     timeline = None
     if args.timeline and op in ("mul", "transpose") and not args.graph:
-        la.mul(y, Aop, x)
+        for _ in range(3):  # steady state, ranks aligned: the timeline is of the last of three back-to-back multiplies
+            barrier()
+            la.mul(y, Aop, x)
+            la.mul(y, Aop, x)
+            la.mul(y, Aop, x)
         tl = la.spmv_timeline(Aop, x)
         rows = [tl] if dist is None else [None] * world
         if dist is not None:
@@ -584,7 +591,9 @@ def main():
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "direct"], help="halo exchange: grouped ncclSend/ncclRecv (default) or the direct peer push")
-    ap.add_argument("--graph", action="store_true", help="replay each multiply (or the whole CG loop) from a CUDA graph")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
+                    help="replay each multiply (or the whole CG loop) from a CUDA graph: hpcla_b200.mul_graph / HPCLA_CG_GRAPH=1 (default)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="plain calls: hpcla_b200.mul, one driver call per launch / event")
     ap.add_argument("--timeline", action="store_true", help="record the per-rank timeline of one multiply (HPCLA_TIMELINE=1) into detail.timeline")
     ap.add_argument("--cpu-workers", type=int, default=0, help="worker threads of the CPU arm (0 = one per host core; 4 for the 2-D Laplacian, as BASELINE.json)")
     args = ap.parse_args()

@@ -347,7 +347,8 @@ extern "C" int hpcla_ctx_init_nccl(hpcla_ctx* ctx, const void* id128) {
     std::memcpy(&id, id128, 128);
     // The halo messages are a few MB at most: a communicator capped at a few CTAs leaves the SMs to the multiply
     // (HPCLA_NCCL_MAX_CTAS, tuning hook; unset = NCCL's default).
-    int max_ctas = 0;
+    // Default 2 (measured, profiles/r2m2_*: 247.9 -> 244.4 us per weak-scaling step at 2 GPUs); 0 = NCCL's own default.
+    int max_ctas = 2;
     if (const char* e = getenv("HPCLA_NCCL_MAX_CTAS")) max_ctas = atoi(e);
     if (max_ctas > 0 && api->CommInitRankConfig) {
         ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
