@@ -591,9 +591,9 @@ def main():
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "direct"], help="halo exchange: grouped ncclSend/ncclRecv (default) or the direct peer push")
-    ap.add_argument("--graph", dest="graph", action="store_true", default=True,
-                    help="replay each multiply (or the whole CG loop) from a CUDA graph: hpcla_b200.mul_graph / HPCLA_CG_GRAPH=1 (default)")
-    ap.add_argument("--no-graph", dest="graph", action="store_false", help="plain calls: hpcla_b200.mul, one driver call per launch / event")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=False,
+                    help="replay each multiply (or the whole CG loop) from a CUDA graph: hpcla_b200.mul_graph / HPCLA_CG_GRAPH=1")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="plain calls: hpcla_b200.mul, one driver call per launch / event (default)")
     ap.add_argument("--timeline", action="store_true", help="record the per-rank timeline of one multiply (HPCLA_TIMELINE=1) into detail.timeline")
     ap.add_argument("--cpu-workers", type=int, default=0, help="worker threads of the CPU arm (0 = one per host core; 4 for the 2-D Laplacian, as BASELINE.json)")
     args = ap.parse_args()

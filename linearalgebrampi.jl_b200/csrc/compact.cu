@@ -297,6 +297,164 @@ __global__ void __launch_bounds__(ROW_THREADS, K >= 8 ? 2 : K >= 4 ? 3 : RowCfg<
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// The same compact tiles behind a RING: one persistent CTA per SM, a producer warp that keeps S tiles in flight (bulk
+// copies of header, positions, values and the x runs of K columns into stage it mod S, completing on full[s]) and eight
+// consumer warps that walk tile after tile out of shared memory and hand each stage back through empty[s].  The copies
+// of the next tiles proceed while a tile is walked, whatever the occupancy — which is what the one-tile-per-CTA kernels
+// above lose when a tile needs a large share of the SM's shared memory (sparse x dense: 100 KB per tile at 8 columns,
+// two CTAs per SM, nothing in flight while both walk).  K = 1 is the plain multiply.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int RING_THREADS = ROW_THREADS + 32;
+
+__device__ __forceinline__ i64 tile_of_pos(const TileRuns& runs, int pos) {
+    int skip = runs.skip[0];
+    if (runs.n > 1) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j) skip = (pos >= runs.cta0[j]) ? runs.skip[j] : skip;
+    }
+    return (i64)(pos + skip);
+}
+
+template <class T, int G, int K>
+__global__ void __launch_bounds__(RING_THREADS, 1) cring_kernel(const CWalkMArgs<T> a, int n_tiles, int stages, int stage_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [stages]
+    uint64_t* empty = full + 8;                              // [stages]  (stages <= 8)
+    unsigned char* ring = smem_raw + 128;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full + s, 32);                // the producer's lanes
+            mbar_init(empty + s, ROW_THREADS / 32);  // one arrival per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int grid = (int)gridDim.x;
+    if (tid >= ROW_THREADS) {
+        // ---------------- producer warp ----------------
+        const int lane = tid - ROW_THREADS;
+        const uint64_t pol = l2_evict_first_policy();
+        int pos = (int)blockIdx.x;
+        int4 run = make_int4(0, 0, 0, 0), run_next = make_int4(0, 0, 0, 0);
+        int4 head_tail = make_int4(0, 0, 0, 0);
+        if (pos < n_tiles) {
+            const unsigned char* gh = a.hdrs + ((i64)a.q0 + pos) * (i64)a.chdr_bytes;
+            run = __ldg(reinterpret_cast<const int4*>(gh + 32) + (lane & (CW_R - 1)));
+        }
+        for (int it = 0; pos < n_tiles; ++it, pos += grid) {
+            const int s = it % stages;
+            const i64 q = (i64)a.q0 + pos;
+            const unsigned char* ghdr = a.hdrs + q * (i64)a.chdr_bytes;
+            if (pos + grid < n_tiles)  // the next tile's run table is requested now: its latency hides behind this tile's issue
+                run_next = __ldg(reinterpret_cast<const int4*>(a.hdrs + (q + grid) * (i64)a.chdr_bytes + 32) + (lane & (CW_R - 1)));
+            const bool x_tail = q >= (i64)a.tail_q_min;
+            if (x_tail) head_tail = __ldg(reinterpret_cast<const int4*>(ghdr) + 1);  // {nruns, x_total, tail_n, tail_soff}
+            if (it >= stages) mbar_wait(empty + s, (uint32_t)((it / stages - 1) & 1));
+            unsigned char* st = ring + (size_t)s * stage_bytes;
+            unsigned short* spos = reinterpret_cast<unsigned short*>(st + a.chdr_bytes);
+            T* sval = reinterpret_cast<T*>(st + a.chdr_bytes + a.cp_bytes);
+            T* sx = sval + a.cw;
+            const i64 tile = tile_of_pos(a.runs, pos);
+            const i64 w0 = tile * (i64)a.window;
+            const i64 left = (a.nnz_total - w0) & ~(i64)3;
+            const int n_fetch = (int)(left < (i64)a.cw ? (left > 0 ? left : 0) : (i64)a.cw);
+            if (lane == 0) {
+                mbar_add_tx(full + s, (uint32_t)a.chdr_fetch + (uint32_t)a.cp_bytes + (uint32_t)n_fetch * (uint32_t)sizeof(T));
+                bulk_g2s(st, ghdr, (uint32_t)a.chdr_fetch, full + s, pol);
+                bulk_g2s(spos, a.colpos + q * (i64)a.cp_bytes, (uint32_t)a.cp_bytes, full + s, pol);
+                if (n_fetch > 0) bulk_g2s(sval, a.nzval + w0, (uint32_t)n_fetch * (uint32_t)sizeof(T), full + s, pol);
+            }
+            if (run.y > 0) {
+                const uint32_t bytes = (uint32_t)run.y * (uint32_t)sizeof(T);
+#pragma unroll
+                for (int idx = lane; idx < K * CW_R; idx += 32) {
+                    const int k = idx / CW_R;
+                    mbar_add_tx(full + s, bytes);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(sx + (size_t)k * a.xcap + run.z)),
+                                 "l"(a.b_own + (i64)k * a.ldb + run.x), "r"(bytes), "r"(smem_u32(full + s))
+                                 : "memory");
+                }
+            }
+            {  // rare: elements no 16-byte copy may fetch (end of x.v: tiles from tail_q_min on; end of A.nzval: last tile)
+                const i64 avail = a.nnz_total - w0;
+                const int n_avail = (int)(avail < (i64)a.cw ? avail : (i64)a.cw);
+                if (x_tail && head_tail.z > 0) {
+                    const int tail_xoff = __ldg(reinterpret_cast<const int*>(ghdr + 32) + 3);
+                    for (int e = lane; e < head_tail.z * K; e += 32) {
+                        const int k = e / head_tail.z, t = e % head_tail.z;
+                        sx[(size_t)k * a.xcap + head_tail.w + t] = a.b_own[(i64)k * a.ldb + tail_xoff + t];
+                    }
+                }
+                for (int kk = n_fetch + lane; kk < n_avail; kk += 32) sval[kk] = a.nzval[w0 + kk];
+            }
+            mbar_arrive(full + s);  // (release: the scalar stores above are visible to whoever sees the phase complete)
+            run = run_next;
+        }
+    } else {
+        // ---------------- consumer warps ----------------
+        constexpr int RPP = ROW_THREADS / G;
+        const int lane = tid % G;
+        int it = 0;
+        for (int pos = (int)blockIdx.x; pos < n_tiles; ++it, pos += grid) {
+            const int s = it % stages;
+            const unsigned char* st = ring + (size_t)s * stage_bytes;
+            const unsigned short* spos = reinterpret_cast<const unsigned short*>(st + a.chdr_bytes);
+            const T* sval = reinterpret_cast<const T*>(st + a.chdr_bytes + a.cp_bytes);
+            const T* sx = sval + a.cw;
+            mbar_wait(full + s, (uint32_t)((it / stages) & 1));
+            const CHead* h = reinterpret_cast<const CHead*>(st);
+            const i64 r0 = h->r0;
+            const int nrows = h->nrows;
+            const unsigned short* off = reinterpret_cast<const unsigned short*>(st + CW_HDR_FIXED);
+            for (int base = 0; base < nrows; base += RPP) {
+                const int i = base + tid / G;
+                const bool valid = i < nrows;
+                const int b = valid ? (int)off[i] : 0;
+                const int e = valid ? (int)off[i + 1] : 0;
+                T acc[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) acc[k] = el_zero(T());
+                if (K == 1) {
+                    constexpr int B = HPCLA_WALK_BATCH;
+                    for (int kk = b + lane; kk < e; kk += B * G) {
+                        T p[B];
+#pragma unroll
+                        for (int u = 0; u < B; ++u) {
+                            const int k2 = kk + u * G;
+                            p[u] = (k2 < e) ? el_mul(sval[k2], sx[spos[k2]]) : el_zero(T());
+                        }
+#pragma unroll
+                        for (int u = 0; u < B; ++u)
+                            if (kk + u * G < e) acc[0] = el_add(acc[0], p[u]);
+                    }
+                } else {
+                    for (int kk = b + lane; kk < e; kk += G) {
+                        const T v = sval[kk];
+                        const T* xp = sx + spos[kk];
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] = el_add(acc[k], el_mul(v, xp[(size_t)k * a.xcap]));
+                    }
+                }
+                if (G > 1) {
+#pragma unroll
+                    for (int m = G / 2; m >= 1; m >>= 1)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) acc[k] = el_add(acc[k], shfl_xor(acc[k], m));
+                }
+                if (valid && lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) st_y(a.c + r0 + i + (i64)k * a.ldc, acc[k]);
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(empty + s);  // this warp is done with the stage
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // set-up: analysis (BUILD = false: stats[i] = {runs, staged x elements}, runs = -1 when the tile cannot be compacted) and
 // construction (BUILD = true) of the compact data of one tile per CTA.  The tile's columns are sorted in shared memory
 // (bitonic), cut into runs wherever two neighbours are more than 64 bytes apart, and every entry's column is replaced by
@@ -564,6 +722,71 @@ static cudaError_t cwalk_m_typed(const CWalkMLaunch& L, cudaStream_t st) {
     if (L.kn == 8) return cwalk_m_lanes<T, 8>(L, st);
     if (L.kn == 4) return cwalk_m_lanes<T, 4>(L, st);
     if (L.kn == 1) return cwalk_m_lanes<T, 1>(L, st);
+    return cudaErrorInvalidValue;
+}
+
+// ring launch: stages = as many tiles as fit the SM's shared memory (at most 8)
+template <class T, int G, int K>
+static cudaError_t cring_launch(const CWalkMLaunch& L, const CWalkMArgs<T>& a, cudaStream_t st) {
+    const size_t stage = cwalk_m_smem_bytes(L.dtype, L.sh, K) - 32;  // multiple of 16
+    int stages = (int)((size_t)(226 * 1024 - 128) / stage);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return cudaErrorInvalidValue;
+    const size_t smem = 128 + (size_t)stages * stage;
+    cudaError_t e;
+    if ((e = ensure_smem<cring_kernel<T, G, K>>(smem, true)) != cudaSuccess) return e;
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!sms[dev & 63]) cudaDeviceGetAttribute(&sms[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    int grid = sms[dev & 63] > 0 ? sms[dev & 63] : 148;
+    if (grid > L.n_launch) grid = L.n_launch;
+    cring_kernel<T, G, K><<<grid, RING_THREADS, smem, st>>>(a, L.n_launch, stages, (int)stage);
+    return cudaGetLastError();
+}
+
+template <class T, int K>
+static cudaError_t cring_lanes(const CWalkMLaunch& L, cudaStream_t st) {
+    CWalkMArgs<T> a;
+    a.nzval = (const T*)L.nzval;
+    a.hdrs = L.hdrs;
+    a.colpos = L.colpos;
+    a.b_own = (const T*)L.b_own + (i64)L.k0 * L.ldb;
+    a.ldb = L.ldb;
+    a.c = (T*)L.c + (i64)L.k0 * L.ldc;
+    a.ldc = L.ldc;
+    a.nnz_total = L.nnz;
+    a.runs = launch_runs(L.n_runs, L.run_cta0, L.run_tile0);
+    a.q0 = L.q0;
+    a.tail_q_min = L.tail_q_min;
+    a.window = L.window;
+    a.cw = L.sh.cw;
+    a.chdr_bytes = L.sh.chdr_bytes;
+    a.chdr_fetch = L.sh.chdr_fetch;
+    a.cp_bytes = L.sh.cp_bytes;
+    a.xcap = L.sh.xcap;
+    switch (L.lanes) {
+        case 1: return cring_launch<T, 1, K>(L, a, st);
+        case 2: return cring_launch<T, 2, K>(L, a, st);
+        case 4: return cring_launch<T, 4, K>(L, a, st);
+        case 8: return cring_launch<T, 8, K>(L, a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <class T>
+static cudaError_t cring_typed(const CWalkMLaunch& L, cudaStream_t st) {
+    if (L.n_launch <= 0) return cudaSuccess;
+    if (L.kn == 8) return cring_lanes<T, 8>(L, st);
+    if (L.kn == 4) return cring_lanes<T, 4>(L, st);
+    if (L.kn == 1) return cring_lanes<T, 1>(L, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cring(const CWalkMLaunch& L, cudaStream_t st) {
+    if (L.dtype == HPCLA_F32) return cring_typed<float>(L, st);
+    if (L.dtype == HPCLA_F64) return cring_typed<double>(L, st);
+    if (L.dtype == HPCLA_C128) return cring_typed<cplx>(L, st);
     return cudaErrorInvalidValue;
 }
 

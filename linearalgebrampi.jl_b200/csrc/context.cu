@@ -92,6 +92,19 @@ NcclApi* nccl_api() {
 // the library does not link libcuda.
 namespace {
 typedef CUresult (*fn_stream_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*fn_stream_write32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+fn_stream_write32 stream_write32() {
+    static fn_stream_write32 fn = []() -> fn_stream_write32 {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (fn_stream_write32)p;
+    }();
+    return fn;
+}
 fn_stream_wait32 stream_wait32() {
     static fn_stream_wait32 fn = []() -> fn_stream_wait32 {
         void* p = nullptr;
@@ -226,6 +239,8 @@ struct hpcla_spmv {
         std::vector<i64> peer_recv_start;    // [nranks] 1-based start, in rank p's gathered, of the segment I fill
         std::vector<void*> ipc_opened;       // mappings to close
         unsigned step = 0;
+        bool memop_failed = false;           // cuStreamWriteValue32 refused the address once: flags are written by a kernel
+        bool consumed_signalled = false;     // this step's "ghosts read" flags went out on the halo stream already
     } direct;
     // compact tiles (compact.cu): headers and 16-bit positions, by position in list [2][0]
     CompactShape csh{};
@@ -347,8 +362,9 @@ extern "C" int hpcla_ctx_init_nccl(hpcla_ctx* ctx, const void* id128) {
     std::memcpy(&id, id128, 128);
     // The halo messages are a few MB at most: a communicator capped at a few CTAs leaves the SMs to the multiply
     // (HPCLA_NCCL_MAX_CTAS, tuning hook; unset = NCCL's default).
-    // Default 2 (measured, profiles/r2m2_*: 247.9 -> 244.4 us per weak-scaling step at 2 GPUs); 0 = NCCL's own default.
-    int max_ctas = 2;
+    // (measured: a cap of 2 gains 1.4 % at 2 GPUs, profiles/r2m2_*, but at 8 GPUs the capped communicator was the slowest
+    // configuration, profiles/r2m8_*: left to NCCL unless asked for)
+    int max_ctas = 0;
     if (const char* e = getenv("HPCLA_NCCL_MAX_CTAS")) max_ctas = atoi(e);
     if (max_ctas > 0 && api->CommInitRankConfig) {
         ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
@@ -1079,14 +1095,28 @@ extern "C" int hpcla_spmv_halo_debug(hpcla_spmv* op, unsigned* out /* [2 * nrank
     return HPCLA_OK;
 }
 
+// Raise a flag (possibly in a peer's memory) behind everything already in the stream: a stream memory operation — no SM, no
+// launch — where the driver accepts one for the address, else a one-thread kernel (HPCLA_HALO_FLAG_KERNEL=1 forces it).
+static int direct_write_flag(hpcla_spmv* op, unsigned* flag, unsigned value, cudaStream_t stream) {
+    static const bool force_kernel = [] { const char* e = getenv("HPCLA_HALO_FLAG_KERNEL"); return e && e[0] == '1'; }();
+    if (!force_kernel && !op->direct.memop_failed) {
+        fn_stream_write32 w = stream_write32();
+        if (w && w((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WRITE_VALUE_DEFAULT) == CUDA_SUCCESS) return HPCLA_OK;
+        op->direct.memop_failed = true;  // (not supported for this memory: the kernel from now on)
+    }
+    CU_TRY(launch_write_flag(flag, value, stream));
+    op->launches += 1;
+    return HPCLA_OK;
+}
+
 // the receiving side of the back-pressure: tell every rank I received from that its data of this step has been read
 static int direct_signal_consumed(hpcla_spmv* op, cudaStream_t stream) {
     auto& D = op->direct;
     if (!D.on) return HPCLA_OK;
     const int P = op->ctx->nranks, me = op->ctx->rank;
     for (const Seg& r : op->recvs) {
-        CU_TRY(launch_write_flag(D.peer_flags[(size_t)r.peer] + P + me, D.step, stream));
-        op->launches += 1;
+        int rc = direct_write_flag(op, D.peer_flags[(size_t)r.peer] + P + me, D.step, stream);
+        if (rc) return rc;
     }
     return HPCLA_OK;
 }
@@ -1142,8 +1172,8 @@ static int exchange_begin(hpcla_spmv* op, const void* d_x, cudaStream_t stream, 
             const bool from_x = !group && op->sends_contiguous;
             const char* src = from_x ? (const char*)d_x + (size_t)(s.src0 - 1) * es : (const char*)op->d_sendbuf + (size_t)s.start * es;
             CU_TRY(cudaMemcpyAsync(D.peer_gathered[(size_t)s.peer] + (size_t)(D.peer_recv_start[(size_t)s.peer] - 1) * es, src, (size_t)s.count * es, cudaMemcpyDefault, hs));
-            CU_TRY(launch_write_flag(D.peer_flags[(size_t)s.peer] + me, step, hs));
-            op->launches += 1;
+            int frc = direct_write_flag(op, D.peer_flags[(size_t)s.peer] + me, step, hs);
+            if (frc) return frc;
         }
         for (const Seg& r : op->recvs)
             if (wait32((CUstream)hs, (CUdeviceptr)(uintptr_t)(D.d_flags + r.peer), step, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
@@ -1245,6 +1275,12 @@ static bool tile_runs(const std::vector<std::pair<int, int>>& runs, int lo, int 
     return n > 0;
 }
 
+// HPCLA_RING: bit 0 = the multiply, bit 1 = sparse x dense on compact tiles run as rings of persistent CTAs
+static int ring_mode() {
+    const char* e = getenv("HPCLA_RING");  // (read per call: a tuning hook, also switched by the tests)
+    return e ? atoi(e) : 0;
+}
+
 // both kernel classes over the interior (which = 0) or boundary (which = 1) tiles
 // (from, to: positions in the lists, per class; nullptr = the whole lists)
 static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t stream, const int* from = nullptr, const int* to = nullptr) {
@@ -1279,6 +1315,19 @@ static int launch_tiles(hpcla_spmv* op, SpmvLaunch& L, int which, cudaStream_t s
             C.y = L.y;
             C.dot_x = L.dot_x;
             C.dot_out = L.dot_out;
+            if ((ring_mode() & 1) && !L.dot_x) {  // the same tiles behind a ring of persistent CTAs (HPCLA_RING, see compact.cu)
+                CWalkMLaunch M;
+                M.dtype = C.dtype, M.lanes = C.lanes, M.window = C.window, M.nzval = C.nzval, M.nnz = C.nnz, M.sh = C.sh;
+                M.hdrs = C.hdrs, M.colpos = C.colpos, M.q0 = C.q0, M.tail_q_min = C.tail_q_min, M.n_runs = C.n_runs;
+                for (int j = 0; j < 9; ++j) M.run_cta0[j] = C.run_cta0[j];
+                for (int j = 0; j < 8; ++j) M.run_tile0[j] = C.run_tile0[j];
+                M.n_launch = C.n_launch, M.b_own = C.x_own, M.ldb = 0, M.c = C.y, M.ldc = 0, M.k0 = 0, M.kn = 1;
+                if (M.lanes <= 8) {
+                    CU_TRY(launch_cring(M, stream));
+                    op->launches += 1;
+                    continue;
+                }
+            }
             CU_TRY(launch_spmv_cwalk(C, stream));
         } else if (c != 1 && runs && !L.has_ghost && op->csr->d_hdrs && !op->dot_request) CU_TRY(launch_spmv_direct(L, stream));
         else if (c != 1) CU_TRY(launch_spmv_rowwalk(L, stream));
@@ -1448,6 +1497,13 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
         if (rc) return rc;
         CU_TRY(cudaEventRecord(op->ev_halo, hs));
         op->halo_recorded = true;
+        if (op->direct.on && op->csr->nlong == 0) {
+            // (direct halo) the boundary tiles were the last readers of the ghosts: tell the senders from here, so that the
+            // caller's stream ends with the interior tiles and not with flag writes
+            rc = direct_signal_consumed(op, hs);
+            if (rc) return rc;
+            op->direct.consumed_signalled = true;
+        }
         if (op->timeline) {
         CU_TRY(cudaEventRecord(op->tl[2], hs));
         op->tl_rec[2] = true;
@@ -1470,8 +1526,11 @@ extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
         rc = launch_long(op, L, stream);
         if (rc) return rc;
     }
-    rc = direct_signal_consumed(op, stream);  // (direct halo) the ghosts of this step have been read
-    if (rc) return rc;
+    if (!op->direct.consumed_signalled) {
+        rc = direct_signal_consumed(op, stream);  // (direct halo) the ghosts of this step have been read
+        if (rc) return rc;
+    }
+    op->direct.consumed_signalled = false;
     if (op->timeline) {
         CU_TRY(cudaEventRecord(op->tl[4], stream));
         op->tl_rec[4] = true;
@@ -1626,7 +1685,8 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
                 M.k0 = L.k0;
                 M.kn = L.kn;
                 if (spmm_cwalk_supported(M)) {
-                    CU_TRY(launch_spmm_cwalk(M, stream));
+                    if (ring_mode() & 2) CU_TRY(launch_cring(M, stream));
+                    else CU_TRY(launch_spmm_cwalk(M, stream));
                     op->launches += 1;
                     continue;
                 }

@@ -171,6 +171,8 @@ struct CWalkMLaunch {
 };
 bool spmm_cwalk_supported(const CWalkMLaunch& L);
 cudaError_t launch_spmm_cwalk(const CWalkMLaunch& L, cudaStream_t st);
+// the same tiles behind a ring: persistent CTAs, producer warp + consumer warps (kn = 1: plain multiply, c = y, b_own = x.v)
+cudaError_t launch_cring(const CWalkMLaunch& L, cudaStream_t st);
 
 // nnz-split multiply for irregular matrices (flat.cu): per-matrix derived structure
 struct FlatData {

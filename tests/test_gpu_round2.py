@@ -107,11 +107,13 @@ def test_csr_create_validates_the_borrowed_arrays():
 @pytest.mark.parametrize("kind,N,T,Ti", [(1, 48, np.float64, np.int32), (1, 41, np.float64, np.int64), (1, 37, np.float32, np.int32),
                                          (2, 24, np.complex128, np.int32), (2, 21, np.float64, np.int64), (0, 301, np.float64, np.int64)])
 @pytest.mark.parametrize("P", [1, 2, 3])
-def test_compact_row_walk(kind, N, T, Ti, P, monkeypatch):
+@pytest.mark.parametrize("ring", [0, 1])
+def test_compact_row_walk(kind, N, T, Ti, P, ring, monkeypatch):
     """Interior tiles of the stencils go through the compact row walk (16-bit positions into bulk-copied runs of x);
     results equal the plain row walk bit for bit (same order of additions), and the oracle within tolerance."""
     S = la.synth
     monkeypatch.setenv("HPCLA_COMPACT", "1")  # (by default only matrices larger than L2 take the compact walk)
+    monkeypatch.setenv("HPCLA_RING", str(ring))
     grid = (N, N) if kind == 0 else N
     n = S.stencil_rows(kind, grid)
     rp, c, v = S.stencil_local(kind, grid, 0, n, T, Ti)
@@ -420,10 +422,13 @@ def test_full_size_powerlaw_20m():
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,N,T,Ti", [(1, 40, np.float64, np.int32), (1, 33, np.float32, np.int64), (2, 20, np.float64, np.int32), (2, 16, np.complex128, np.int64)])
 @pytest.mark.parametrize("P", [1, 2])
-def test_sparse_times_dense_on_compact_tiles(kind, N, T, Ti, P, monkeypatch):
+@pytest.mark.parametrize("ring", [0, 3])
+def test_sparse_times_dense_on_compact_tiles(kind, N, T, Ti, P, ring, monkeypatch):
     """A * B::HPCMatrix with the interior tiles on the compact kernel (x runs of all columns staged by bulk copies):
-    every column equals A * B[:, k] bit for bit, 13 columns = one pass of 8, one of 4 and one single column."""
+    every column equals A * B[:, k] bit for bit, 13 columns = one pass of 8, one of 4 and one single column.
+    ring = 3: the same tiles behind rings of persistent CTAs (producer warp + consumer warps), multiply and product."""
     monkeypatch.setenv("HPCLA_COMPACT", "1")
+    monkeypatch.setenv("HPCLA_RING", str(ring))
     S = la.synth
     n = S.stencil_rows(kind, N)
     ncols = 13
