@@ -459,7 +459,7 @@ def run_b200_arm(args, spec):
 
     # ---- end to end: host (pinned) x in, host y out, every step ---------------------------------------------------
     e2e = None
-    if op not in ("cg", "spmm"):
+    if op not in ("cg", "spmm") and not args.no_e2e:
         # pinned host buffers allocated and first-touched next to this rank's GPU (hpcla_host_alloc)
         hx, hy = la.host_buffer(backend, x.local_size), la.host_buffer(backend, y.local_size)
         hx.array[:] = x.local_values()
@@ -590,6 +590,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="poisson256")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-in / host-out leg (experiments only: a line without e2e is not a bench line)")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "direct"], help="halo exchange: grouped ncclSend/ncclRecv (default) or the direct peer push")
     ap.add_argument("--graph", dest="graph", action="store_true", default=False,
                     help="replay each multiply (or the whole CG loop) from a CUDA graph: hpcla_b200.mul_graph / HPCLA_CG_GRAPH=1")
