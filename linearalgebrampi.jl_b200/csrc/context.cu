@@ -513,6 +513,23 @@ int ctx_rank_info(const hpcla_ctx* ctx, int* device, int* rank, int* nranks, int
     return HPCLA_OK;
 }
 
+// max over the ranks of a small non-negative status (NCCL world; the value itself on a single rank): how a rank-local
+// failure inside a collective set-up routine is made known to everybody before the next exchange is entered
+int ctx_agree_max(hpcla_ctx* ctx, int local, int* out, cudaStream_t stream) {
+    if (!ctx || !out) return fail(HPCLA_ERR_ARG, "ctx_agree_max: null");
+    *out = local;
+    if (ctx->nranks == 1 || !ctx->comm) return HPCLA_OK;
+    int* d = reinterpret_cast<int*>(ctx->d_red_out + 4);  // (second half of the 8-double result slot)
+    int* h = reinterpret_cast<int*>(ctx->h_red_out + 4);
+    *h = local;
+    CU_TRY(cudaMemcpyAsync(d, h, sizeof(int), cudaMemcpyHostToDevice, stream));
+    NCCL_TRY(nccl_api()->AllReduce(d, d, 1, ncclInt32, ncclMax, ctx->comm, stream));
+    CU_TRY(cudaMemcpyAsync(h, d, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    *out = *h;
+    return HPCLA_OK;
+}
+
 int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, const i64* send_bytes, void* d_recv, const i64* recv_off,
                        const i64* recv_bytes, cudaStream_t stream) {
     if (!ctx) return fail(HPCLA_ERR_ARG, "ctx_exchange_bytes: null");

@@ -225,6 +225,7 @@ cudaError_t launch_long_rows(const LongRowsLaunch& L, cudaStream_t st);
 // context.cu, for the other translation units: who am I, and an all-to-all of byte ranges between device buffers
 // (grouped ncclSend/ncclRecv; the range for my own rank is a device-to-device copy).  NCCL world or nranks == 1.
 int ctx_rank_info(const hpcla_ctx* ctx, int* device, int* rank, int* nranks, int* has_comm);
+int ctx_agree_max(hpcla_ctx* ctx, int local, int* out, cudaStream_t stream);
 int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, const i64* send_bytes, void* d_recv, const i64* recv_off,
                        const i64* recv_bytes, cudaStream_t stream);
 

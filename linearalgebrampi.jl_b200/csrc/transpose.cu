@@ -220,8 +220,19 @@ int transpose_typed(hpcla_ctx* ctx, int rank, int nranks, bool has_comm, const i
         std::vector<i64> recv_off((size_t)nranks + 1, 0);
         for (int q = 0; q < nranks; ++q) recv_counts[(size_t)q] = (i64)rcounts[(size_t)q], recv_off[(size_t)q + 1] = recv_off[(size_t)q] + recv_counts[(size_t)q];
         total = recv_off[(size_t)nranks];
-        CU_TRY(S.alloc(&d_rkeys, sizeof(u64) * (size_t)total));
-        CU_TRY(S.alloc(&d_rvals, sizeof(T) * (size_t)total));
+        // receive buffers: a rank that cannot allocate them must not simply return — the others would wait for it in the
+        // exchanges below — so the ranks agree on the worst status first
+        cudaError_t ae = S.alloc(&d_rkeys, sizeof(u64) * (size_t)total);
+        if (ae == cudaSuccess) ae = S.alloc(&d_rvals, sizeof(T) * (size_t)total);
+        const int local_bad = (ae != cudaSuccess || total >= (i64)INT32_MAX) ? 1 : 0;
+        if (ae != cudaSuccess) cudaGetLastError();
+        int any_bad = 0;
+        rc = ctx_agree_max(ctx, local_bad, &any_bad, st);
+        if (rc) return rc;
+        if (any_bad)
+            return fail(local_bad ? (ae != cudaSuccess ? HPCLA_ERR_NOMEM : HPCLA_ERR_ARG) : HPCLA_ERR_STATE,
+                        "hpcla_transpose_device: %s", local_bad ? (ae != cudaSuccess ? "out of device memory for the received entries" : "more than 2^31 - 1 entries on one rank")
+                                                                : "another rank could not hold its share of the transpose");
         std::vector<i64> so((size_t)nranks), sb((size_t)nranks), ro((size_t)nranks), rb((size_t)nranks);
         for (int pass = 0; pass < 2; ++pass) {
             const i64 w = pass == 0 ? (i64)sizeof(u64) : (i64)sizeof(T);

@@ -88,8 +88,17 @@ class MatrixPlan:
         # memoised symbolic product
         L = _lib.lib()
         h = ctypes.c_void_p()
-        _lib.check(L.hpcla_spgemm_symbolic(_lib.itype_code(b.Ti), A.nrows_local, _lib.ptr(np.ascontiguousarray(A.rowptr)), _lib.ptr(np.ascontiguousarray(A.colval)),
-                                           len(need), _lib.ptr(self.bg_rowptr), _lib.ptr(self.bg_cols), ctypes.byref(h)))
+        rc = L.hpcla_spgemm_symbolic(_lib.itype_code(b.Ti), A.nrows_local, _lib.ptr(np.ascontiguousarray(A.rowptr)), _lib.ptr(np.ascontiguousarray(A.colval)),
+                                     len(need), _lib.ptr(self.bg_rowptr), _lib.ptr(self.bg_cols), ctypes.byref(h))
+        # a rank-local failure (out of memory for the term lists) must not leave the other ranks waiting in the value exchange
+        # of the first product: every rank learns the worst status before anyone goes on
+        msg = (L.hpcla_last_error() or b"").decode() if rc else ""
+        statuses = comm_allgather(b.comm, (int(rc), msg))
+        bad = [(q, st) for q, st in enumerate(statuses) if st[0] != 0]
+        if bad:
+            if h.value:
+                L.hpcla_spgemm_destroy(h)
+            raise _lib.HPCLAError("MatrixPlan: the symbolic product failed on rank(s) " + ", ".join(f"{q} [status {st[0]}: {st[1]}]" for q, st in bad))
         self.handle = h.value
         nnz, ncc, nterms = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         _lib.check(L.hpcla_spgemm_sizes(self.handle, ctypes.byref(nnz), ctypes.byref(ncc), ctypes.byref(nterms)))
