@@ -310,6 +310,7 @@ static int set_device(const hpcla_ctx* ctx) {
 // context
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int hpcla_ctx_create(int device, int rank, int nranks, hpcla_ctx** out) {
+    NvtxRange nvtx_range("hpcla_ctx_create");
     if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(HPCLA_ERR_ARG, "hpcla_ctx_create: bad arguments");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -352,6 +353,7 @@ extern "C" int hpcla_nccl_unique_id(void* id128) {
 }
 
 extern "C" int hpcla_ctx_init_nccl(hpcla_ctx* ctx, const void* id128) {
+    NvtxRange nvtx_range("hpcla_ctx_init_nccl");
     if (!ctx || !id128) return fail(HPCLA_ERR_ARG, "hpcla_ctx_init_nccl: null");
     if (ctx->comm || ctx->group) return fail(HPCLA_ERR_STATE, "hpcla_ctx_init_nccl: the context already has a world");
     NcclApi* api = nccl_api();
@@ -556,6 +558,7 @@ int ctx_exchange_bytes(hpcla_ctx* ctx, const void* d_send, const i64* send_off, 
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int hpcla_csr_create(hpcla_ctx* ctx, int dtype, int itype, int64_t nrows, int64_t ncc, int64_t nnz, const void* d_rowptr,
                                 const void* d_colval, const void* d_nzval, hpcla_csr** out) {
+    NvtxRange nvtx_range("hpcla_csr_create");
     if (!ctx || !out || nrows < 0 || ncc < 0 || nnz < 0 || !d_rowptr) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: bad arguments");
     if (!dtype_size(dtype) || !itype_size(itype)) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: unknown dtype/itype");
     if (nnz > 0 && (!d_colval || !d_nzval)) return fail(HPCLA_ERR_ARG, "hpcla_csr_create: null colval/nzval");
@@ -808,6 +811,7 @@ static int build_compact(hpcla_spmv* op, std::vector<int> (&lists)[3][2]) {
 }
 
 extern "C" int hpcla_spmv_create(hpcla_ctx* ctx, hpcla_csr* A, const hpcla_plan* plan, int64_t n_x_local, hpcla_spmv** out) {
+    NvtxRange nvtx_range("hpcla_spmv_create");
     if (!ctx || !A || !plan || !out || n_x_local < 0) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: bad arguments");
     if (A->ctx != ctx) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: the matrix belongs to another context");
     if (plan->n_gathered != A->ncc) return fail(HPCLA_ERR_ARG, "hpcla_spmv_create: plan gathers %lld elements but A has %lld compressed columns", (long long)plan->n_gathered, (long long)A->ncc);
@@ -1047,6 +1051,7 @@ extern "C" int hpcla_spmv_halo_export(hpcla_spmv* op, void* blob_out) {
 }
 
 extern "C" int hpcla_spmv_halo_connect(hpcla_spmv* op, const void* blobs) {
+    NvtxRange nvtx_range("hpcla_spmv_halo_connect");
     if (!op || !blobs) return fail(HPCLA_ERR_ARG, "hpcla_spmv_halo_connect: null");
     if (!op->direct.d_flags) return fail(HPCLA_ERR_STATE, "hpcla_spmv_halo_connect: call hpcla_spmv_halo_export first");
     int rc = set_device(op->ctx);
@@ -1434,6 +1439,7 @@ static int launch_long(hpcla_spmv* op, const SpmvLaunch& base, cudaStream_t stre
 }
 
 extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void* stream_) {
+    NvtxRange nvtx_range("hpcla_spmv_begin");
     if (!op || (op->n_x_local > 0 && !d_x) || (op->csr->nrows > 0 && !d_y)) return fail(HPCLA_ERR_ARG, "hpcla_spmv_begin: null");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_begin: the previous call was not finished");
     int rc = set_device(op->ctx);
@@ -1493,6 +1499,7 @@ extern "C" int hpcla_spmv_begin(hpcla_spmv* op, const void* d_x, void* d_y, void
 }
 
 extern "C" int hpcla_spmv_finish(hpcla_spmv* op) {
+    NvtxRange nvtx_range("hpcla_spmv_finish");
     if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_finish: null");
     if (op->phase != 1) return fail(HPCLA_ERR_STATE, "hpcla_spmv_finish: no multiply in flight");
     int rc = set_device(op->ctx);
@@ -1582,6 +1589,7 @@ extern "C" int hpcla_spmv_timeline(hpcla_spmv* op, double* ms4_out) {
 // launch instead of ~10 driver calls — what the latency-bound strong-scaling regime needs.
 // NCCL world or a single rank.  capture: (re)builds the graph; launch: replays it on `stream`.
 extern "C" int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d_y, void* stream_) {
+    NvtxRange nvtx_range("hpcla_spmv_graph_capture");
     if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmv_graph_capture: null");
     if (op->ctx->group && op->ctx->nranks > 1 && op->has_peers) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: needs an NCCL world or a single rank");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_capture: the previous call was not finished");
@@ -1621,6 +1629,7 @@ extern "C" int hpcla_spmv_graph_capture(hpcla_spmv* op, const void* d_x, void* d
 }
 
 extern "C" int hpcla_spmv_graph_launch(hpcla_spmv* op, void* stream_) {
+    NvtxRange nvtx_range("hpcla_spmv_graph_launch");
     if (!op || !op->graph) return fail(HPCLA_ERR_STATE, "hpcla_spmv_graph_launch: no captured graph");
     int rc = set_device(op->ctx);
     if (rc) return rc;
@@ -1718,6 +1727,7 @@ static int spmm_tiles(hpcla_spmv* op, int which, bool ghost, cudaStream_t stream
 }
 
 extern "C" int hpcla_spmm_begin(hpcla_spmv* op, const void* d_B, int64_t ldb, void* d_C, int64_t ldc, int ncols, void* stream_) {
+    NvtxRange nvtx_range("hpcla_spmm_begin");
     if (!op || ncols < 0 || (op->n_x_local > 0 && ncols > 0 && !d_B) || (op->csr->nrows > 0 && ncols > 0 && !d_C)) return fail(HPCLA_ERR_ARG, "hpcla_spmm_begin: bad arguments");
     if (ldb < op->n_x_local || ldc < op->csr->nrows) return fail(HPCLA_ERR_ARG, "hpcla_spmm_begin: leading dimensions smaller than the local blocks");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmm_begin: the previous call was not finished");
@@ -1782,6 +1792,7 @@ extern "C" int hpcla_spmm_begin(hpcla_spmv* op, const void* d_B, int64_t ldb, vo
 }
 
 extern "C" int hpcla_spmm_finish(hpcla_spmv* op) {
+    NvtxRange nvtx_range("hpcla_spmm_finish");
     if (!op) return fail(HPCLA_ERR_ARG, "hpcla_spmm_finish: null");
     if (op->phase != 3) return fail(HPCLA_ERR_STATE, "hpcla_spmm_finish: no product in flight");
     int rc = set_device(op->ctx);
@@ -1909,6 +1920,7 @@ static int build_pipe(hpcla_spmv* op) {
 }
 
 extern "C" int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x, void* d_y, void* h_y, void* stream_) {
+    NvtxRange nvtx_range("hpcla_spmv_run_staged");
     if (!op || (op->n_x_local > 0 && (!h_x || !d_x)) || (op->csr->nrows > 0 && (!h_y || !d_y))) return fail(HPCLA_ERR_ARG, "hpcla_spmv_run_staged: null");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_run_staged: the previous call was not finished");
     hpcla_ctx* ctx = op->ctx;
@@ -1995,6 +2007,7 @@ extern "C" int hpcla_spmv_run_staged(hpcla_spmv* op, const void* h_x, void* d_x,
 }
 
 extern "C" int hpcla_spmv_gather(hpcla_spmv* op, const void* d_x, void* stream_, void** d_gathered_out) {
+    NvtxRange nvtx_range("hpcla_spmv_gather");
     if (!op || !d_gathered_out) return fail(HPCLA_ERR_ARG, "hpcla_spmv_gather: null");
     if (op->phase != 0) return fail(HPCLA_ERR_STATE, "hpcla_spmv_gather: the previous call was not finished");
     int rc = set_device(op->ctx);
@@ -2100,6 +2113,7 @@ extern "C" int hpcla_axpby(hpcla_ctx* ctx, int dtype, int64_t n, const void* alp
 extern "C" int hpcla_repartition_run(hpcla_ctx* ctx, int dtype, int64_t n_send, const int64_t* send_rank_ids, const int64_t* send_first,
                                      const int64_t* send_count, int64_t n_recv, const int64_t* recv_rank_ids, const int64_t* recv_count,
                                      const int64_t* recv_offset, const int64_t* local3, const void* d_src, void* d_dst, void* stream_) {
+    NvtxRange nvtx_range("hpcla_repartition_run");
     if (!ctx || !dtype_size(dtype) || n_send < 0 || n_recv < 0 || !local3) return fail(HPCLA_ERR_ARG, "hpcla_repartition_run: bad arguments");
     if ((n_send > 0 || n_recv > 0) && !ctx->comm) return fail(HPCLA_ERR_STATE, "hpcla_repartition_run: the plan exchanges data but the context has no NCCL communicator");
     int rc = set_device(ctx);
@@ -2150,6 +2164,7 @@ static int cg_enqueue(hpcla_spmv* op, const void* d_b, void* d_x, char* r, char*
 }
 
 extern "C" int hpcla_cg(hpcla_spmv* op, const void* d_b, void* d_x, void* d_work, int iters, double* rr_history_out, void* stream_) {
+    NvtxRange nvtx_range("hpcla_cg");
     if (!op || !d_b || !d_x || !d_work || iters < 0) return fail(HPCLA_ERR_ARG, "hpcla_cg: bad arguments");
     hpcla_ctx* ctx = op->ctx;
     const int dtype = op->csr->dtype;
