@@ -453,3 +453,63 @@ def test_next_row_entry_points_reject_bad_arguments():
     nnz, ncc, nt = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
     assert L.hpcla_spgemm_sizes(h, ctypes.byref(nnz), ctypes.byref(ncc), ctypes.byref(nt)) == 0 and (nnz.value, ncc.value, nt.value) == (2, 2, 2)
     L.hpcla_spgemm_destroy(h)
+
+
+def test_plan_import_round_trip_on_the_host():
+    """hpcla_plan_import is a host function: a plan built by the reference's algorithm (the oracle), handed over in Ti width
+    (Int32 and Int64), comes back out of hpcla_plan_get field by field exactly as it went in — the route of the Julia binding,
+    checked here without a device (the device half is tests/test_gpu_round2.py::test_plan_import_route)."""
+    import ctypes
+
+    L = la._lib.lib()
+    rng = np.random.default_rng(4)
+    G = sp.random(500, 420, density=0.03, random_state=rng, format="csr")
+    for P in (1, 2, 4):
+        xp = np.concatenate([[1], np.sort(rng.integers(1, 421, size=P - 1)), [421]]).astype(np.int64)
+        for itype, Ti in (("i32", np.int32), ("i64", np.int64)):
+            plans = orc.vector_plans(orc.distribute(G, P, itype=itype), xp)
+            for rank, o in enumerate(plans):
+                sidx = [np.ascontiguousarray(a, dtype=Ti) for a in o.send_indices]
+                rprm = [np.ascontiguousarray(a, dtype=Ti) for a in o.recv_perm]
+                slen = np.array([len(a) for a in sidx], dtype=np.int64)
+                rlen = np.array([len(a) for a in rprm], dtype=np.int64)
+                sids = np.ascontiguousarray(o.send_rank_ids, dtype=np.int64)
+                rids = np.ascontiguousarray(o.recv_rank_ids, dtype=np.int64)
+                lsrc = np.ascontiguousarray(o.local_src_indices, dtype=Ti)
+                ldst = np.ascontiguousarray(o.local_dst_indices, dtype=Ti)
+                n_x = int(xp[rank + 1] - xp[rank])
+                ph = ctypes.c_void_p()
+                la._lib.check(L.hpcla_plan_import(rank, P, la._lib.itype_code(Ti), o.n_gathered, n_x, len(sids), la._lib.ptr(sids), la._lib.ptr(slen),
+                                                  la._lib.ptr_array(sidx), len(rids), la._lib.ptr(rids), la._lib.ptr(rlen), la._lib.ptr_array(rprm), len(lsrc),
+                                                  la._lib.ptr(lsrc), la._lib.ptr(ldst), ctypes.byref(ph)))
+                plan = la.VectorPlan(ph.value, Ti, n_x)
+                assert plan.send_rank_ids.tolist() == sids.tolist() and plan.recv_rank_ids.tolist() == rids.tolist()
+                assert np.array_equal(plan.local_src_indices, lsrc) and np.array_equal(plan.local_dst_indices, ldst)
+                assert all(np.array_equal(a, b) for a, b in zip(plan.send_indices, sidx)) and len(plan.send_indices) == len(sidx)
+                assert all(np.array_equal(a, b) for a, b in zip(plan.recv_perm, rprm)) and len(plan.recv_perm) == len(rprm)
+                assert plan.n_gathered == o.n_gathered and plan.local_src_indices.dtype == np.dtype(Ti)
+
+
+def test_bench_describes_the_workloads_consistently():
+    """bench.py's closed forms (rows, nnz per workload) equal what the generators produce, both arms print the same `config`,
+    and the algorithmic bytes follow SURVEY §8(d)."""
+    import importlib.util
+
+    import hpcla_synth
+
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for name, n_gpus in [("poisson256", 1), ("poisson256", 8), ("laplace2d-1000", 1), ("stencil27-192", 1), ("poisson512-strong", 8), ("cg-512", 8)]:
+        w = bench.workload_spec(name, n_gpus)
+        n, nnz = bench.workload_counts(w)
+        assert n == hpcla_synth.stencil_rows(w["kind"], w["grid"])
+        small = tuple(min(g, 12) for g in w["grid"])
+        ws = dict(w, grid=small)
+        ns, nnzs = bench.workload_counts(ws)
+        assert nnzs == int(hpcla_synth.lib().hpcla_synth_stencil_nnz(w["kind"], *small, 0, ns))
+        cfg = bench.shared_config(w, n, nnz, n_gpus)
+        assert set(cfg) == {"workload", "index_type", "op", "rows", "nnz", "l2"} and cfg["rows"] == n and cfg["nnz"] == nnz
+    b, f = bench.algorithmic_bytes_flops(16777216, 16777216, 117047296, "f64", "i32", "mul")
+    assert b == 1740111876 and f == 234094592  # BASELINE.md §2, config 2
+    assert bench.workload_counts(bench.workload_spec("poisson256", 8)) == (134217728, 937951232)  # config 5
