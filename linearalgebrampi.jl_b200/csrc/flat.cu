@@ -423,23 +423,32 @@ cudaError_t flat_build(int itype, const void* rowptr, i64 nrows, i64 nnz, FlatDa
     F->n_chunks = (nnz + FLAT_CHUNK - 1) / FLAT_CHUNK;
     F->n_wchunks = (nnz + FLAT_WCHUNK - 1) / FLAT_WCHUNK;  // warp chunks that hold entries
     cudaError_t e;
+    struct Temps {  // scratch of this function, released on every way out (what lands in *F is released by flat_free)
+        void* p[3] = {nullptr, nullptr, nullptr};
+        ~Temps() {
+            for (void* q : p) cudaFree(q);
+        }
+    } temps;
     if ((e = cudaMalloc(&F->d_bits, sizeof(unsigned) * (size_t)F->n_chunks * FLAT_WORDS)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(F->d_bits, 0, sizeof(unsigned) * (size_t)F->n_chunks * FLAT_WORDS, st)) != cudaSuccess) return e;
     if ((e = cudaMalloc(&F->d_wrow, sizeof(i64) * (size_t)F->n_chunks * (FLAT_THREADS / 32))) != cudaSuccess) return e;
     unsigned char* d_ne = nullptr;
     if ((e = cudaMalloc(&d_ne, (size_t)nrows)) != cudaSuccess) return e;
+    temps.p[0] = d_ne;
     const int blocks = (int)((nrows + 255) / 256);
     if (itype == HPCLA_I32) flat_bits_kernel<int><<<blocks, 256, 0, st>>>((const int*)rowptr, nrows, F->d_bits, d_ne);
     else flat_bits_kernel<long long><<<blocks, 256, 0, st>>>((const long long*)rowptr, nrows, F->d_bits, d_ne);
     // ordinals among the non-empty rows (exclusive scan of the flags); only kept when some row is empty
     i64* d_ord = nullptr;
     if ((e = cudaMalloc(&d_ord, sizeof(i64) * (size_t)(nrows + 1))) != cudaSuccess) return e;
+    temps.p[1] = d_ord;
     {
         cub::TransformInputIterator<i64, NonEmptyAsI64, cub::CountingInputIterator<i64>> in(cub::CountingInputIterator<i64>(0), NonEmptyAsI64{d_ne});
         void* tmp = nullptr;
         size_t tmp_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, in, d_ord, nrows, st);
         if ((e = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) return e;
+        temps.p[2] = tmp;
         e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, in, d_ord, nrows, st);
         if (e != cudaSuccess) return e;
         i64 last_ord = 0;
@@ -447,7 +456,6 @@ cudaError_t flat_build(int itype, const void* rowptr, i64 nrows, i64 nnz, FlatDa
         if ((e = cudaMemcpyAsync(&last_ord, d_ord + (nrows - 1), sizeof(i64), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaMemcpyAsync(&last_ne, d_ne + (nrows - 1), 1, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        cudaFree(tmp);
         F->n_nonempty = last_ord + (last_ne ? 1 : 0);
     }
     const bool has_empty = F->n_nonempty < nrows;
@@ -462,8 +470,6 @@ cudaError_t flat_build(int itype, const void* rowptr, i64 nrows, i64 nnz, FlatDa
     }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    cudaFree(d_ne);
-    cudaFree(d_ord);
     return cudaSuccess;
 }
 
