@@ -627,6 +627,11 @@ def materialize_transpose(A: HPCSparseMatrix) -> HPCSparseMatrix:
     rank, P = comm_rank(comm), comm_size(comm)
     if b.is_cuda and os.environ.get("HPCLA_TRANSPOSE", "device") != "host" and (P == 1 or b.ctx().world == "nccl"):
         Y = _materialize_transpose_device(A)
+        # The structural hash is a cache key (src/sparse.jl:97-121), and the structure of A^T is a function of the structure
+        # of A: derive Y's key from A's instead of hashing ~|A| bytes of read-back arrays a second time on the host (the
+        # larger part of the first transpose(A)*x at BASELINE config 3).  Same on every rank (A's hash is the all-gathered
+        # one); a matrix with the same structure built another way only misses the plan cache, it can never hit wrongly.
+        Y.structural_hash = _digest(b"hpcla:transpose-of:", _ensure_hash(A))
         A.cached_transpose = Y
         Y.cached_transpose = A
         return Y
